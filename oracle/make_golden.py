@@ -1,0 +1,178 @@
+"""Generate tests/golden/*.npz from the LIVE reference (CPU torch, fp32, 1 thread).
+
+TEST INFRASTRUCTURE ONLY; runs only where /root/reference is mounted (the build container).
+The reference holds no golden vectors of its own, so these files ARE the
+parity pin: every tensor below is produced by calling the unmodified reference modules
+through oracle/ref_harness.py.  Re-run with ``python -m oracle.make_golden``.
+
+Weights: ``lpd_pretrained_weights.npz`` holds the 12 ``emb_nn.*`` tensors of the reference's
+only shipped checkpoint (pretrained/lpd-pretrained.t7, data not source) so that the GPU
+box -- which has no /root/reference -- can rebuild the same synthetic 59-key checkpoint:
+``synth.make_checkpoint(1234, emb_weights=lpd)``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness, synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+OV2 = synth.OVERLAP2_0575
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def N_(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name:28s} {os.path.getsize(path) / 1e6:7.2f} MB  " +
+          " ".join(f"{k}{tuple(v.shape)}" for k, v in arrs.items()))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    ref = ref_harness.import_reference()
+    U, LP, TR, VM = ref.util, ref.lpdnet_model, ref.transformer, ref.vcrnet_model
+
+    # ---- weights -------------------------------------------------------------------------
+    lpd_sd = torch.load(os.path.join(ref_harness.REF_ROOT, "pretrained", "lpd-pretrained.t7"),
+                        map_location="cpu", weights_only=True)
+    lpd = {k: N_(v).astype(np.float32) for k, v in lpd_sd.items()}
+    save("lpd_pretrained_weights", **lpd)
+    ckpt = synth.make_checkpoint(1234, emb_weights=lpd)
+    sd_t = synth.checkpoint_to_torch(ckpt)
+
+    def build(partial):
+        args = ref_harness.default_args(partial=partial, overlap2=OV2 if partial else 0.75)
+        net = VM.VCRNet(args).eval()
+        ref_keys = list(net.state_dict().keys())
+        assert ref_keys == list(ckpt.keys()), "synthetic checkpoint key order != reference"
+        net.load_state_dict(sd_t, strict=True)
+        return net
+
+    net_w, net_p = build(False), build(True)
+    save("state_dict_layout", keys=np.array(list(ckpt.keys())),
+         shapes=np.array([str(tuple(v.shape)) for v in ckpt.values()]))
+
+    rs = np.random.RandomState(7)
+    with torch.no_grad():
+        # ---- kNN ---------------------------------------------------------------------------
+        x3g = synth.grid_cloud(rs, (2, 3, 512), 8, -0.5, 0.5)
+        x64g = synth.grid_cloud(rs, (2, 64, 256), 6, -2.0, 2.0)
+        pairs = synth.make_pairs(2, 1024)
+        x3f = pairs["src"]
+        f64 = N_(F.leaky_relu(net_w.emb_nn.conv2_lpd(F.leaky_relu(net_w.emb_nn.conv1_lpd(T(x3f)), 0.0)), 0.0))
+        save("knn", x3g=x3g, idx3g=N_(U.knn(T(x3g), 20)), x64g=x64g, idx64g=N_(U.knn(T(x64g), 20)),
+             x3f=x3f, idx3f=N_(U.knn(T(x3f), 20)), x64f=f64, idx64f=N_(U.knn(T(f64), 20)))
+        gf = N_(U.get_graph_feature(T(x64g[:1, :8, :64]), k=5))
+        save("graph_feature", x=x64g[:1, :8, :64], k=np.array(5), out=gf)
+
+        # ---- FPS ---------------------------------------------------------------------------
+        pg = synth.grid_cloud(rs, (4, 3, 1024), 8, -0.5, 0.5)
+        pg2 = synth.grid_cloud(rs, (2, 3, 768), 8, -0.5, 0.5)
+        pf = synth.make_pairs(3, 1024, first_item=5)["tgt"]
+        save("fps", pg=pg, ig=N_(U.farthest_point_sample(T(pg), 32)),
+             pg2=pg2, ig2=N_(U.farthest_point_sample(T(pg2), 32)),
+             pf=pf, i_f=N_(U.farthest_point_sample(T(pf), 32)))
+
+        # ---- LPDNet ------------------------------------------------------------------------
+        xl = synth.make_pairs(1, 512, first_item=3)["src"]
+        emb0 = net_w.emb_nn
+        h = F.leaky_relu(emb0.conv2_lpd(F.leaky_relu(emb0.conv1_lpd(T(xl)), 0.0)), 0.0)
+        args = ref_harness.default_args()
+        emb02 = LP.LPDNet(args, negative_slope=0.2).eval()
+        emb02.load_state_dict({k[len("emb_nn."):]: v for k, v in lpd_sd.items()})
+        h02 = F.leaky_relu(emb02.conv2_lpd(F.leaky_relu(emb02.conv1_lpd(T(xl)), 0.2)), 0.2)
+        save("lpdnet", x=xl, out_s0=N_(emb0(T(xl))), out_s02=N_(emb02(T(xl))),
+             idx_feat_s0=N_(U.knn(h, 20)), idx_feat_s02=N_(U.knn(h02, 20)), idx_xyz=N_(U.knn(T(xl), 20)))
+
+        # ---- Transformer (whole + partial) ----------------------------------------------------
+        pr = synth.make_pairs(1, 256, first_item=11)
+        se, te = emb0(T(pr["src"])), emb0(T(pr["tgt"]))
+        sp, tp = net_w.pointer(se, te)
+        spp, tpp = net_p.pointer(se, te)
+        save("transformer", src_emb=N_(se), tgt_emb=N_(te), src_p=N_(sp), tgt_p=N_(tp),
+             src_p_partial=N_(spp), tgt_p_partial=N_(tpp), overlap2=np.array(OV2))
+
+        ln = TR.LayerNorm(512)
+        ln.a_2.data = torch.from_numpy(rs.randn(512).astype(np.float32))
+        ln.b_2.data = torch.from_numpy(rs.randn(512).astype(np.float32))
+        xln = rs.randn(3, 17, 512).astype(np.float32) * 3 + 1
+        save("layernorm", x=xln, a=N_(ln.a_2), b=N_(ln.b_2), out=N_(ln(T(xln))))
+
+        q = rs.randn(2, 4, 96, 128).astype(np.float32)
+        k = rs.randn(2, 4, 80, 128).astype(np.float32)
+        v = rs.randn(2, 4, 80, 128).astype(np.float32)
+        o0, p0 = TR.attention(T(q), T(k), T(v))
+        o1, p1 = TR.attention(T(q), T(k), T(v), is_src=True, overlap2=OV2)
+        save("attention", q=q, k=k, v=v, out=N_(o0), out_src=N_(o1), overlap2=np.array(OV2),
+             colsum=N_(p0.sum(dim=(1, 2))), kept=N_((p1.sum(dim=(1, 2)) > 0)))
+
+        # ---- VCP head ----------------------------------------------------------------------
+        se2, te2 = se + sp, te + tp
+        s_a, c_a = net_w.head(se2, te2, T(pr["src"]), T(pr["tgt"]))
+        hp = net_p.head
+        so, seo, to, teo, _, _ = hp.selectCom(T(pr["src"]), se2, T(pr["tgt"]), te2, overlap2=OV2)
+        s_p, c_p = hp.getCopair(so, seo, to, teo, OV2)
+        save("vcp_head", src=pr["src"], tgt=pr["tgt"], src_emb=N_(se2), tgt_emb=N_(te2),
+             corr_all=N_(c_a), sel_src=N_(so), sel_tgt=N_(to), sel_src_emb=N_(seo), sel_tgt_emb=N_(teo),
+             part_src=N_(s_p), part_corr=N_(c_p), overlap2=np.array(OV2))
+
+        # ---- SVD head ----------------------------------------------------------------------
+        ps = synth.make_pairs(8, 128, first_item=20)
+        a = ps["src"]
+        b = ps["tgt"] + rs.randn(*ps["tgt"].shape).astype(np.float32) * 0.01
+        b[4:6] = b[4:6] * np.array([1, 1, -1], np.float32).reshape(1, 3, 1)   # mirrored => det<0 branch
+        b[6] = rs.randn(3, 128).astype(np.float32)                            # unrelated clouds
+        a[7, 2] = 0.0                                                         # planar source => rank-2 H
+        R, t = net_w.svd(T(a), T(b))
+        save("svd_head", src=a, corr=b, R=N_(R), t=N_(t))
+
+        # ---- full network -------------------------------------------------------------------
+        pw = synth.make_pairs(2, 512, first_item=30)
+        outs = VM.vcrnetIter(net_w, T(pw["src"]), T(pw["tgt"]), iter=1)
+        se_w = emb0(T(pw["src"]))
+        save("vcrnet_whole", src=pw["src"], tgt=pw["tgt"], R_gt=pw["R_ab"], t_gt=pw["t_ab"],
+             srcK=N_(outs[0]), corrK=N_(outs[1]), R_ab=N_(outs[2]), t_ab=N_(outs[3]),
+             R_ba=N_(outs[4]), t_ba=N_(outs[5]), src_emb0=N_(se_w))
+        outs2 = VM.vcrnetIter(net_w, T(pw["src"]), T(pw["tgt"]), iter=2)
+        save("vcrnet_whole_iter2", R_ab=N_(outs2[2]), t_ab=N_(outs2[3]), corrK=N_(outs2[1]))
+
+        pp = synth.make_pairs(2, 512, partial=True, first_item=40)
+        outp1 = VM.vcrnetIter(net_p, T(pp["src"]), T(pp["tgt"]), iter=1)
+        outp = VM.vcrnetIter(net_p, T(pp["src"]), T(pp["tgt"]), iter=3)
+        save("vcrnet_partial", src=pp["src"], tgt=pp["tgt"], R_gt=pp["R_ab"], t_gt=pp["t_ab"],
+             overlap2=np.array(OV2),
+             srcK1=N_(outp1[0]), corrK1=N_(outp1[1]), R_ab1=N_(outp1[2]), t_ab1=N_(outp1[3]),
+             srcK=N_(outp[0]), corrK=N_(outp[1]), R_ab=N_(outp[2]), t_ab=N_(outp[3]),
+             R_ba=N_(outp[4]), t_ba=N_(outp[5]))
+
+        # ---- LPD pre-train forward (loss) ------------------------------------------------------
+        pa = synth.make_pairs(2, 512, aligned=True, first_item=50)
+        largs = ref_harness.default_args(model="lpd", num_points=512)
+        lnet = LP.LPD(largs).eval()
+        lnet.load_state_dict(lpd_sd, strict=True)
+        se_l, te_l, loss, mse, mae = lnet(T(pa["src"]), T(pa["tgt"]))
+        save("lpd_loss", src=pa["src"], tgt=pa["tgt"], loss=N_(loss), mse=N_(mse), mae=N_(mae),
+             src_emb=N_(se_l))
+
+
+if __name__ == "__main__":
+    main()
