@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- registration pairs/sec of the B200-native VCR-Net inference path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" = one pass of the hot path (vcrnetIter: LPDNet embedding of both clouds ->
+Transformer pointer -> VCP head -> SVD head, all --iter iterations) over one batch of synthetic
+ModelNet40-shaped pairs.  Workload at every N: BASELINE.json configs[0] "whole-to-whole, 1024 pts,
+batch 16" per GPU (weak scaling: each rank registers its own batch, no collective on the data
+path); `--workload partial` runs configs[1] (overlap 0.575 crops -> 768 pts, --iter 3, batch 24).
+
+  value     pairs/s with inputs resident in HBM, CUDA events per step, L2 flushed between steps
+  e2e       same metric through the public module API from pinned HOST buffers (H2D + D2H timed)
+  roofline  dominant kernel: algorithmic FLOP/launch / CUDA-event launch time vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (numpy restatement of the reference) on this box's host cores,
+                bounded sample; `--impl reference` makes that the measured arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="whole", choices=["whole", "partial"])
+    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: config's)")
+    ap.add_argument("--num-points", type=int, default=1024)
+    ap.add_argument("--precision", default=os.environ.get("VCR_PRECISION", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_cfg(a):
+    from oracle import synth
+    if a.workload == "whole":
+        return dict(name="VCR-Net whole-to-whole eval, synthetic ModelNet40-shaped pairs, 1024 pts, iter=1",
+                    partial=False, iters=1, batch=a.batch or 16, overlap2=0.75, reserve=1.0)
+    return dict(name="VCR-Net partial-to-partial eval, overlap=0.575 crops (768 of 1024 pts), iter=3",
+                partial=True, iters=3, batch=a.batch or 24, overlap2=synth.OVERLAP2_0575,
+                reserve=synth.RESERVE_0575)
+
+
+def load_ckpt():
+    from oracle import synth
+    lpd = dict(np.load(os.path.join(ROOT, "tests", "golden", "lpd_pretrained_weights.npz")))
+    return synth.make_checkpoint(1234, emb_weights=lpd)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, bounded sample
+# ------------------------------------------------------------------------------------------------
+
+def cpu_pairs_per_sec(cfg, num_points, n_pairs, repeats=1):
+    from oracle import synth
+    from oracle import vcr_oracle as O
+    ckpt = load_ckpt()
+    p = synth.make_pairs(n_pairs, num_points, partial=cfg["partial"], reserve=cfg["reserve"] if cfg["partial"] else 1.0)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.vcrnet_iter(ckpt, p["src"], p["tgt"], cfg["iters"], partial=cfg["partial"], overlap2=cfg["overlap2"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_pairs / best, best
+
+
+def run_reference_arm(a, cfg, rank, world):
+    if rank != 0:
+        return
+    times = []
+    n = a.cpu_sample_pairs
+    for i in range(a.warmup + a.steps):
+        v, dt = cpu_pairs_per_sec(cfg, a.num_points, n)
+        if i >= a.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = n / (ms / 1e3)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "batch_per_step": n, "num_points": a.num_points},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} pairs per step through oracle/vcr_oracle.py (numpy restatement of the "
+                                   f"reference; the reference is Python/torch and cannot travel to this box)"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def gemm_flops(args):
+    M, N, K, nbo, nbi = args[18:23]
+    return 2.0 * M * N * K * nbo * nbi
+
+
+def run_gpu_arm(a, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import vcr_net_b200 as V
+    from vcr_net_b200._lib import lib
+    from oracle import synth
+    from oracle.ref_harness import default_args
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=b200) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    ckpt = load_ckpt()
+    net = V.VCRNet(default_args(partial=cfg["partial"], overlap2=cfg["overlap2"])).to(dev).eval()
+    net.load_state_dict(synth.checkpoint_to_torch(ckpt), strict=True)
+    B = cfg["batch"]
+    # each rank registers its own pairs (weak scaling; items rank*B .. rank*B+B-1), a few distinct batches
+    nbatches = 2
+    host = []
+    for j in range(nbatches):
+        p = synth.make_pairs(B, a.num_points, partial=cfg["partial"], reserve=cfg["reserve"] if cfg["partial"] else 1.0,
+                             first_item=(rank * nbatches + j) * B)
+        host.append((torch.from_numpy(p["src"]).pin_memory(), torch.from_numpy(p["tgt"]).pin_memory()))
+    devb = [(s.to(dev), t.to(dev)) for s, t in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        s, t = devb[i % nbatches]
+        return V.vcrnetIter(net, s, t, iter=cfg["iters"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            step(i)
+        barrier()
+        clocks = Clocks(local_rank)
+        clocks.start()
+        # ---- device-resident timing -------------------------------------------------------------
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        l0 = L.vcr_launch_count()
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(a.steps):
+            flush.fill_(float(i))                     # L2 flush, outside the per-step event bracket
+            ev[i][0].record(stream)
+            step(i)
+            ev[i][1].record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = L.vcr_launch_count() - l0
+        ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
+        ms_total = sum(ms_steps)
+        # ---- end-to-end: pinned host -> device -> path -> host, through the module API -------------
+        R_host = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
+        t_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+        sbuf, tbuf = torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])
+
+        def e2e_step(i):
+            hs, ht = host[i % nbatches]
+            sbuf.copy_(hs, non_blocking=True)
+            tbuf.copy_(ht, non_blocking=True)
+            out = V.vcrnetIter(net, sbuf, tbuf, iter=cfg["iters"])
+            R_host.copy_(out[2], non_blocking=True)
+            t_host.copy_(out[3], non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        for i in range(a.steps):
+            flush.fill_(float(i))
+            ee[i][0].record(stream)
+            e2e_step(i)
+            ee[i][1].record(stream)
+        barrier()
+        ms_e2e = sum(e0.elapsed_time(e1) for e0, e1 in ee)
+        clk = clocks.stop()
+        # ---- per-kernel CUDA-event profile of the same step (roofline leg) --------------------------
+        L.profile_begin()
+        nprof = 3
+        for i in range(nprof):
+            flush.fill_(1.0)
+            step(i)
+        prof = L.profile_end()
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs_total = B * a.steps * world
+    value = pairs_total / (ms_total / 1e3)
+    e2e_value = pairs_total / (ms_e2e / 1e3)
+    M = devb[0][0].shape[2]
+
+    # roofline: aggregate per C-ABI entry point
+    agg = {}
+    for name, ms, args in prof:
+        d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+        d["ms"] += ms; d["n"] += 1
+        if name == "vcr_gemm_f32":
+            d["flops"] += gemm_flops(args)
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    step_ms_prof = sum(d["ms"] for d in agg.values()) / nprof
+    roof = {"kernel": top[0], "launches_per_step": top[1]["n"] / nprof, "share_of_step": top[1]["ms"] / nprof / step_ms_prof,
+            "avg_launch_ms": top[1]["ms"] / top[1]["n"], "traffic": None}
+    if top[1]["flops"] > 0:
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12
+        roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                    note="fp32 SIMT FFMA kernel measured against the dense bf16 tensor peak")
+    else:
+        roof.update(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs", 6650.0), unit="GB/s", frac=None)
+    breakdown = {k: round(v["ms"] / nprof, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+
+    line = {
+        "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "batch_per_gpu": B, "num_points": a.num_points, "points_in_net": M,
+                   "iter": cfg["iters"], "precision": a.precision, "parallelism": f"batch-shard x{world}, no collective",
+                   "l2": "flushed between timed steps (256 MB fill)", "weights": "synthetic 59-key checkpoint"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * M * 4,
+                "d2h_bytes_per_step": B * 12 * 4, "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "kernel_ms_per_step": breakdown,
+        "wall_s_timed_region": t_wall,
+    }
+    if not a.no_cpu_baseline:
+        v, dt = cpu_pairs_per_sec(cfg, a.num_points, a.cpu_sample_pairs)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{a.cpu_sample_pairs} pairs of the same workload, one pass of "
+                                          f"oracle/vcr_oracle.py (numpy), {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched as plain `python bench.py --gpus N`: re-exec one rank per GPU
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                                  str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
+    cfg = workload_cfg(a)
+    if a.impl == "reference":
+        run_reference_arm(a, cfg, rank, world)
+    else:
+        run_gpu_arm(a, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

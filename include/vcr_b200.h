@@ -1,0 +1,136 @@
+/*
+ * vcr_b200 -- C ABI of the B200-native (sm_100a) VCR-Net registration inference path.
+ *
+ * The reference (qiaozhijian/VCR-Net) is pure Python/PyTorch and has no FFI or operator
+ * registry: its hot path reaches the GPU only through ATen calls inside the functions cited
+ * below.  Each entry point here replaces the ATen call sequence of one such call site.  The
+ * host side stays Python (vcr_net_b200/, same class / function names as the reference) and
+ * binds this header through ctypes (vcr_net_b200/_lib.py parses THIS file for the signatures).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), caller-allocated, never retained;
+ *   - no hidden allocation, no synchronisation, no global mutable state: calls are thread-safe
+ *     and asynchronous on `stream` of the CURRENT device (nn.DataParallel's per-device threads);
+ *   - workspace comes from the caller; query its size with the matching *_workspace_bytes();
+ *   - return value: 0 = VCR_OK, < 0 = error (the Python wrapper raises RuntimeError):
+ *       -1 invalid argument / alignment, -2 unsupported shape, -3 launch failure, -4 workspace;
+ *   - "token-major" = [B, N, C] row-major (a point's channels contiguous); "channel-major" =
+ *     the reference's [B, C, N].
+ * Reference citations are relative to the reference repository root.
+ */
+#ifndef VCR_B200_H
+#define VCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* ---- bookkeeping --------------------------------------------------------------------------------
+ * vcr_launch_count: kernels launched by this library in this process so far (bench.py gpu_launches). */
+long long vcr_launch_count(void);
+int vcr_abi_version(void);
+
+/* ---- kNN graph: util/util.py:143-160 knn(x,k) -------------------------------------------------
+ * pd_ij = (-xx_j - (-2 x_i.x_j)) - xx_i, neighbours = ranks 1..k of the descending order (rank 0
+ * dropped exactly like `topk(k+1)[..., 1:]`), ties -> lower index.  x: [B,D,N] (token_major=0) or
+ * [B,N,D] (token_major=1); D in {3,64}; 1<=k<=31; idx32 / idx64: [B,N,k], either may be NULL. */
+size_t vcr_knn_workspace_bytes(int B, int N);
+int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
+                 int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- get_graph_feature: util/util.py:176-199 ---------------------------------------------------
+ * xt token-major [B,N,D]; idx [B,N,k]; out [B,2D,N,k] contiguous = concat(x[idx], x centre). */
+int vcr_graph_feature(const float* xt, int B, int D, int N, int k, const int* idx, float* out,
+                      cudaStream_t stream);
+
+/* ---- FPS: util/util.py:107-140 farthest_point_sample (== util/fps.py:10-49) ---------------------
+ * xyz [B,3,N] -> idx [B,npoint]; N <= 14000. */
+int vcr_fps(const float* xyz, int B, int N, int npoint, int32_t* idx32, int64_t* idx64, cudaStream_t stream);
+
+/* ---- generic fp32 GEMM with fused epilogue -------------------------------------------------------
+ * Replaces nn.Conv1d/Conv2d(kernel 1)/nn.Linear (model/lpdnet_model.py:111-135,
+ * model/transformer.py:210-224,238) and the torch.matmul calls of attention
+ * (model/transformer.py:30,55) and of the VCP head (model/vcrnet_model.py:337).
+ * C[z] = act(alpha * A[z](MxK) * op(B[z]) + bias[n]) + residual[z][m,n];  b_layout 0: B is [N,K],
+ * 1: B is [K,N]; z = outer*nb_inner + inner with element strides s?o / s?i; act 0 none, 1 LeakyReLU. */
+int vcr_gemm_f32(const float* A, int lda, long long sAo, long long sAi,
+                 const float* B, int ldb, long long sBo, long long sBi, int b_layout,
+                 float* C, int ldc, long long sCo, long long sCi,
+                 const float* bias, const float* residual, int ldr, long long sRo, long long sRi,
+                 int M, int N, int K, int nb_outer, int nb_inner,
+                 float alpha, int act, float slope, cudaStream_t stream);
+
+/* ---- LPDNet pieces: model/lpdnet_model.py:103-137 ------------------------------------------------
+ * conv1_lpd (:111): xyz [B,3,N] -> token-major out[B*N, ldo] = LeakyReLU(W[Cout,3] p + bias). */
+int vcr_conv3_act(const float* xyz, const float* w, const float* bias, int B, int N, int Cout, float slope,
+                  float* out, int ldo, cudaStream_t stream);
+/* convDG1 + max + convDG2 + max (:122-126) from PQ = [P | Q] (P = W_a f, Q = W_b f + bias, both 128
+ * wide): x1 = max_k act(P[j]+Q[i]), x2 = act(max_k W2 e1 + b2).  k must be 20; idx is per-cloud local. */
+int vcr_edgeconv_dg(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts,
+                    const float* W2, const float* b2, float slope, float* x1, int ld1, float* x2, int ld2,
+                    cudaStream_t stream);
+/* convSN1 + max (:130-132): out = act(max_k P[idx] + Q), C in {128,256,384,512}. */
+int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, const int* idx, int k, int N,
+                   long long total_pts, int C, float slope, float* out, int ldo, cudaStream_t stream);
+
+/* ---- Transformer pieces: model/transformer.py -----------------------------------------------------
+ * LayerNorm (:134-144): a*(x-mean)/(std_unbiased+eps)+b (+ residual if not NULL). D%128==0, D<=1024. */
+int vcr_layernorm(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                  const float* residual, int ldr, float* out, int ldo, cudaStream_t stream);
+/* softmax over the last dim, in place (:34); keep[batch,n]==0 keys are set to -1e9 first (:51-52). */
+int vcr_softmax_rows(float* S, int ld, long long rows, int n, const uint8_t* keep, long long rows_per_batch,
+                     cudaStream_t stream);
+/* column sums of probabilities over heads and queries (:39) / over sources (vcrnet_model.py:222). */
+size_t vcr_colsum_workspace_bytes(int B, int n);
+int vcr_colsum(const float* P, int ld, int B, long long rows_per_batch, int n, float* out, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream);
+int vcr_rowsum(const float* P, int ld, long long rows, int n, float* out, cudaStream_t stream);
+/* top-K (value desc, ties -> lower index): sorted indices and/or a uint8 membership mask (:41-47). */
+int vcr_topk_select(const float* vals, int B, int n, int K, int* idx_out, uint8_t* mask_out, cudaStream_t stream);
+
+/* ---- VcpTopK head: model/vcrnet_model.py:162-347 ---------------------------------------------------
+ * Row pass over dot[B,Ns,ld] = s_i.t_j: pd = (-xx_i + 2 dot) - yy_j, softmax over j, then
+ * mode 0 (:344-345) corr[B,3,Ns] = sum_j P_ij tgt[B,3,Nt];  mode 1 (:221) P in place;
+ * mode 2 (:295-299) best_idx = argmax_j, best_val = max_j P_ij. */
+int vcr_sqnorm_rows(const float* X, int ld, long long rows, int D, float* out, cudaStream_t stream);
+int vcr_softcorr_rows(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
+                      const float* tgt, int mode, float* corr, int* best_idx, float* best_val, cudaStream_t stream);
+int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy, cudaStream_t stream);
+/* row sums of the softmax taken over sources (dim=1) (:243-244); workspace 2*B*Nt floats. */
+int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+int vcr_gather_rows(const float* in, int ld_in, int B, int Nin, const int* idx, int K, int C, float* out,
+                    int ld_out, cudaStream_t stream);
+int vcr_gather_cols(const float* in, int B, int C, int Nin, const int* idx, int K, float* out, cudaStream_t stream);
+/* getCopair's output gathers (:300-331, tgtK==1): src_out[b,:,r] = src[b,:,keep[b,r]],
+ * corr_out[b,:,r] = tgt[b,:,best_idx[b,keep[b,r]]];  src [B,3,Ns], tgt [B,3,Nt], outputs [B,3,K]. */
+int vcr_copair_gather(const float* src, const float* tgt, int B, int Ns, int Nt, const int* keep,
+                      const int* best_idx, int K, float* src_out, float* corr_out, cudaStream_t stream);
+
+/* ---- SVD head + pose algebra: model/vcrnet_model.py:350-399, :515-516, :21-43; util/util.py:91-96 --
+ * src, corr [B,3,M] -> R_ab [B,3,3], t_ab [B,3]; optional R_ba = R^T, t_ba = -R^T t, H (covariance). */
+int vcr_svd_head(const float* src, const float* corr, int B, int M, float* R_ab, float* t_ab,
+                 float* R_ba, float* t_ba, float* H_out, cudaStream_t stream);
+int vcr_rigid_apply(const float* pc, const float* R, const float* t, int B, int N, float* out, cudaStream_t stream);
+int vcr_pose_compose(const float* R_i, const float* t_i, float* R_f, float* t_f, int B, cudaStream_t stream);
+int vcr_pose_inverse(const float* R, const float* t, float* R_inv, float* t_inv, int B, cudaStream_t stream);
+/* host-side entry to the same 3x3 Jacobi SVD routine the kernel uses (unit tests; no GPU needed). */
+int vcr_host_svd3(const double* H, double* U, double* S, double* V);
+
+/* ---- layout / elementwise helpers -------------------------------------------------------------------
+ * in [nb,R,C] (row stride ld_in) -> out [nb,C,R]: the .transpose(2,1).contiguous() of the reference. */
+int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, int ld_out,
+                  long long stride_in, long long stride_out, cudaStream_t stream);
+int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCR_B200_H */

@@ -1,0 +1,88 @@
+"""CPU checks of the boundary: the C-ABI library loads, exports every symbol include/vcr_b200.h
+declares, the product never touches oracle/ and has no CPU fallback, state_dict layout matches."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_header_symbols_exported():
+    from vcr_net_b200._lib import LIB_PATH, parse_header
+    protos = parse_header()
+    assert len(protos) >= 28
+    cdll = ctypes.CDLL(LIB_PATH)
+    for name in protos:
+        assert hasattr(cdll, name), name
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vcr_net_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert "/root/reference" not in txt, f
+
+
+def test_no_cpu_fallback():
+    import vcr_net_b200 as V
+    from oracle.ref_harness import default_args
+    net = V.VCRNet(default_args())
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64), torch.zeros(1, 3, 64))
+    with pytest.raises(RuntimeError):
+        V.knn(torch.zeros(1, 3, 64), 20)
+    with pytest.raises(RuntimeError):
+        V.farthest_point_sample(torch.zeros(1, 3, 64), 4)
+
+
+def test_state_dict_layout_and_t7_roundtrip(tmp_path, ckpt):
+    import vcr_net_b200 as V
+    from oracle import synth
+    from oracle.ref_harness import default_args
+    g = load_golden("state_dict_layout")
+    net = V.VCRNet(default_args())
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in g["shapes"]]
+    # legacy (non-zip) pickle, the reference's .t7 format; loads with strict=False like util/initPara.py:254
+    path = str(tmp_path / "model.t7")
+    torch.save(synth.checkpoint_to_torch(ckpt), path, _use_new_zipfile_serialization=False)
+    res = net.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    lpd = {k: torch.from_numpy(v) for k, v in load_golden("lpd_pretrained_weights").items()}
+    res = net.load_state_dict(lpd, strict=False)          # lpd-pretrained seeds emb_nn only
+    assert not res.unexpected_keys and len(res.missing_keys) == 59 - 12
+    lpdm = V.LPD(default_args())
+    lpdm.load_state_dict(lpd, strict=True)
+    assert lpdm.emb_nn.negative_slope == 0.2 and net.emb_nn.negative_slope == 0.0
+
+
+def test_host_svd_matches_numpy():
+    from vcr_net_b200._lib import lib
+    L = lib()
+    rs = np.random.RandomState(0)
+    for trial in range(200):
+        H = rs.randn(3, 3)
+        if trial % 5 == 0:
+            H[:, 2] = H[:, 0] * 0.5 + H[:, 1]            # rank 2
+        if trial % 17 == 0:
+            H = np.outer(rs.randn(3), rs.randn(3))       # rank 1
+        U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        L.vcr_host_svd3(p(H), p(U), p(S), p(V))
+        assert np.allclose(S, np.linalg.svd(H)[1], atol=1e-12)
+        assert np.allclose(U @ np.diag(S) @ V.T, H, atol=1e-12)
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-10) and np.allclose(V.T @ V, np.eye(3), atol=1e-10)

@@ -1,0 +1,488 @@
+// Row-wise / elementwise kernels of the path (HBM-bound by construction): layout changes at the
+// module boundary, the 3->64 pointwise conv, the reference's custom LayerNorm, row softmax (with the
+// partial-overlap key mask), column statistics of attention probabilities, and the soft
+// virtual-correspondence reduction.  One warp per row, float4 accesses, no shared memory.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// [B,C,N] <-> [B,N,C] through a 32x32 smem tile (both sides coalesced)
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
+                                 int ld_in, int ld_out, long long s_in, long long s_out) {
+    // in: [R, Cc] (row stride ld_in)  ->  out: [Cc, R] (row stride ld_out), per batch blockIdx.z
+    __shared__ float t[32][33];
+    const float* ib = in + blockIdx.z * s_in;
+    float* ob = out + blockIdx.z * s_out;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) t[i][threadIdx.x] = ib[(size_t)r * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) ob[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1_lpd: [B,3,N] channel-major xyz -> token-major [B*N, Cout], LeakyReLU
+// (model/lpdnet_model.py:111).  Accumulation order c = 0,1,2 then + bias like a GEMM with bias.
+// ---------------------------------------------------------------------------------------------
+__global__ void conv3_kernel(const float* __restrict__ xyz, const float* __restrict__ w /*[Cout,3]*/,
+                             const float* __restrict__ bias, int N, int Cout, float slope,
+                             float* __restrict__ out, int ldo) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.y + threadIdx.y;
+    if (n >= N) return;
+    const float* p = xyz + (size_t)b * 3 * N;
+    const float x = p[n], y = p[N + n], z = p[2 * N + n];
+    float* o = out + ((size_t)b * N + n) * ldo;
+    for (int c = threadIdx.x; c < Cout; c += 32) {
+        float acc = w[c * 3 + 0] * x;
+        acc = fmaf(w[c * 3 + 1], y, acc);
+        acc = fmaf(w[c * 3 + 2], z, acc);
+        o[c] = leaky(acc + bias[c], slope);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm of model/transformer.py:141-144: a*(x-mean)/(std_unbiased+eps)+b.  D % 128 == 0, D <= 1024.
+// ---------------------------------------------------------------------------------------------
+template <int VPL>  // float4 per lane
+__global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
+                                 const float* __restrict__ b, float eps, int M, int D,
+                                 const float* __restrict__ res, int ldr, float* __restrict__ out, int ldo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i] = xr[lane + i * 32];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float stdv = sqrtf(warp_sum(q) / (float)(D - 1));
+    const float den = stdv + eps;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* o = reinterpret_cast<float4*>(out + (size_t)row * ldo);
+    const float4* rr = res ? reinterpret_cast<const float4*>(res + (size_t)row * ldr) : nullptr;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 aa = a4[lane + i * 32], bb = b4[lane + i * 32];
+        float4 r;
+        r.x = aa.x * v[i].x / den + bb.x;
+        r.y = aa.y * v[i].y / den + bb.y;
+        r.z = aa.z * v[i].z / den + bb.z;
+        r.w = aa.w * v[i].w / den + bb.w;
+        if (rr) {
+            const float4 e = rr[lane + i * 32];
+            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+        }
+        o[lane + i * 32] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-place row softmax over S[rows, n] (row stride ld).  keep (optional): uint8 [batch, n], the row's
+// batch is row / rows_per_batch; keys with keep == 0 are filled with -1e9 before the softmax exactly
+// as model/transformer.py:51-52 does.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(float* __restrict__ S, int ld, long long rows, int n,
+                                    const uint8_t* __restrict__ keep, long long rows_per_batch) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* r = S + row * ld;
+    const uint8_t* kp = keep ? keep + (row / rows_per_batch) * n : nullptr;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        const float e = expf(v - m);
+        r[j] = e;
+        s += e;
+    }
+    s = warp_sum(s);
+    for (int j = lane; j < n; j += 32) r[j] = r[j] / s;
+}
+
+// colsum[b, j] = sum over the rows of batch b of P[row, j]   (model/transformer.py:39 and
+// model/vcrnet_model.py:222).  Deterministic: a thread owns a column and walks its rows in order,
+// rows are split into `gridDim.y` slabs per batch whose partials are added in slab order by pass 2.
+__global__ void colsum_partial_kernel(const float* __restrict__ P, int ld, long long rows_per_batch, int n,
+                                      int slabs, float* __restrict__ part /*[B, slabs, n]*/) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slab = blockIdx.y, b = blockIdx.z;
+    if (j >= n) return;
+    const long long per = (rows_per_batch + slabs - 1) / slabs;
+    const long long r0 = slab * per, r1 = min(rows_per_batch, r0 + per);
+    const float* p = P + ((long long)b * rows_per_batch) * ld + j;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    long long r = r0;
+    for (; r + 3 < r1; r += 4) {
+        a0 += p[(r + 0) * ld]; a1 += p[(r + 1) * ld]; a2 += p[(r + 2) * ld]; a3 += p[(r + 3) * ld];
+    }
+    for (; r < r1; ++r) a0 += p[r * ld];
+    part[((size_t)b * slabs + slab) * n + j] = (a0 + a1) + (a2 + a3);
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int slabs, int n, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= n) return;
+    float s = 0.f;
+    for (int t = 0; t < slabs; ++t) s += part[((size_t)b * slabs + t) * n + j];
+    out[(size_t)b * n + j] = s;
+}
+
+// rowsum[r] = sum_j P[r, j]   (model/vcrnet_model.py:244 after the dim=1 softmax)
+__global__ void rowsum_kernel(const float* __restrict__ P, int ld, long long rows, int n, float* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* r = P + row * ld;
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) s += r[j];
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+
+// squared row norms, plain fp32 (used by the VCP head: model/vcrnet_model.py:338-339)
+__global__ void sqnorm_rows_kernel(const float* __restrict__ X, int ld, long long rows, int D, float* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* r = reinterpret_cast<const float4*>(X + row * ld);
+    float s = 0.f;
+    for (int j = lane; j < D / 4; j += 32) {
+        const float4 v = r[j];
+        s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VCP head row pass (model/vcrnet_model.py:341-345): given dot[i,j] = s_i . t_j,
+//   pd_ij = (-xx_i - (-2 dot_ij)) - yy_j ; P = softmax_j(pd) ; corr[:, i] = sum_j P_ij tgt[:, j].
+// mode 0: write corr (soft correspondence, whole).  mode 1: write P in place (partial selectCom needs
+// the matrix for column/row statistics).  mode 2: write (argmax_j, max_j P_ij) (partial getCopair).
+// ---------------------------------------------------------------------------------------------
+__global__ void softcorr_rows_kernel(float* __restrict__ dot, int ld, int Ns, int Nt,
+                                     const float* __restrict__ xx, const float* __restrict__ yy,
+                                     const float* __restrict__ tgt /*[B,3,Nt]*/, int mode,
+                                     float* __restrict__ corr /*[B,3,Ns]*/,
+                                     int* __restrict__ best_idx, float* __restrict__ best_val) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= Ns) return;
+    float* r = dot + ((size_t)b * Ns + i) * ld;
+    const float* yb = yy + (size_t)b * Nt;
+    const float nx = -xx[(size_t)b * Ns + i];
+    float m = -INFINITY;
+    int mj = 0x7fffffff;
+    for (int j = lane; j < Nt; j += 32) {
+        const float pd = __fsub_rn(__fsub_rn(nx, -2.f * r[j]), yb[j]);
+        r[j] = pd;
+        if (pd > m) { m = pd; mj = j; }
+    }
+    // arg-max with ties -> lower index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
+        if (om > m || (om == m && oj < mj)) { m = om; mj = oj; }
+    }
+    float s = 0.f;
+    for (int j = lane; j < Nt; j += 32) {
+        const float e = expf(r[j] - m);
+        r[j] = e;
+        s += e;
+    }
+    s = warp_sum(s);
+    if (mode == 0) {
+        const float* tb = tgt + (size_t)b * 3 * Nt;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        for (int j = lane; j < Nt; j += 32) {
+            const float pj = r[j] / s;
+            cx = fmaf(pj, tb[j], cx);
+            cy = fmaf(pj, tb[Nt + j], cy);
+            cz = fmaf(pj, tb[2 * Nt + j], cz);
+        }
+        cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz);
+        if (lane == 0) {
+            float* cb = corr + (size_t)b * 3 * Ns;
+            cb[i] = cx; cb[Ns + i] = cy; cb[2 * Ns + i] = cz;
+        }
+    } else if (mode == 1) {
+        for (int j = lane; j < Nt; j += 32) r[j] = r[j] / s;
+    } else {
+        if (lane == 0) {
+            best_idx[(size_t)b * Ns + i] = mj;
+            best_val[(size_t)b * Ns + i] = 1.0f / s;       // exp(0)/s, the max probability
+        }
+    }
+}
+
+// column softmax statistics for selectCom's second pass (model/vcrnet_model.py:243-244):
+//   rowsum_i = sum_j softmax over i (dim=1) of pd_ij.  Needs column max and column sum-exp first.
+// Thread-per-column kernels over the pd matrix (coalesced along j).
+__global__ void col_lse_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt,
+                               float* __restrict__ cmax, float* __restrict__ csum) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Nt) return;
+    const float* p = pd + (size_t)b * Ns * ld + j;
+    float m = -INFINITY;
+    for (int i = 0; i < Ns; ++i) m = fmaxf(m, p[(size_t)i * ld]);
+    float s = 0.f;
+    for (int i = 0; i < Ns; ++i) s += expf(p[(size_t)i * ld] - m);
+    cmax[(size_t)b * Nt + j] = m;
+    csum[(size_t)b * Nt + j] = s;
+}
+__global__ void rowsum_colsoftmax_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt,
+                                         const float* __restrict__ cmax, const float* __restrict__ csum,
+                                         float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= Ns) return;
+    const float* r = pd + ((size_t)b * Ns + i) * ld;
+    const float* cm = cmax + (size_t)b * Nt;
+    const float* cs = csum + (size_t)b * Nt;
+    float s = 0.f;
+    for (int j = lane; j < Nt; j += 32) s += expf(r[j] - cm[j]) / cs[j];
+    s = warp_sum(s);
+    if (lane == 0) out[(size_t)b * Ns + i] = s;
+}
+
+// pd matrix only (no softmax): pd_ij = (-xx_i + 2 dot_ij) - yy_j, in place
+__global__ void negdist_kernel(float* __restrict__ dot, int ld, int Ns, int Nt, const float* __restrict__ xx,
+                               const float* __restrict__ yy) {
+    const int b = blockIdx.z;
+    const int i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Nt) return;
+    float* r = dot + ((size_t)b * Ns + i) * ld;
+    r[j] = __fsub_rn(__fsub_rn(-xx[(size_t)b * Ns + i], -2.f * r[j]), yy[(size_t)b * Nt + j]);
+}
+
+// gather rows: out[b, r, :] = in[b, idx[b, r], :]   (C % 4 == 0)
+__global__ void gather_rows_kernel(const float* __restrict__ in, int ld_in, int Nin, const int* __restrict__ idx,
+                                   int K, int C, float* __restrict__ out, int ld_out) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= K) return;
+    const int src = idx[(size_t)b * K + r];
+    const float4* s = reinterpret_cast<const float4*>(in + ((size_t)b * Nin + src) * ld_in);
+    float4* d = reinterpret_cast<float4*>(out + ((size_t)b * K + r) * ld_out);
+    for (int c = lane; c < C / 4; c += 32) d[c] = s[c];
+}
+
+// gather columns of a channel-major cloud: out[b, c, r] = in[b, c, idx[b, r]]
+__global__ void gather_cols_kernel(const float* __restrict__ in, int Cc, int Nin, const int* __restrict__ idx,
+                                   int K, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= K) return;
+    const int src = idx[(size_t)b * K + r];
+    for (int c = 0; c < Cc; ++c)
+        out[((size_t)b * Cc + c) * K + r] = in[((size_t)b * Cc + c) * Nin + src];
+}
+
+// getCopair's final gathers (model/vcrnet_model.py:300-331, tgtK == 1 so the weight is exactly 1)
+__global__ void copair_gather_kernel(const float* __restrict__ src, const float* __restrict__ tgt, int Ns, int Nt,
+                                     const int* __restrict__ keep, const int* __restrict__ best, int K,
+                                     float* __restrict__ so, float* __restrict__ co) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= K) return;
+    const int si = keep[(size_t)b * K + r];
+    const int ti = best[(size_t)b * Ns + si];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        so[((size_t)b * 3 + c) * K + r] = src[((size_t)b * 3 + c) * Ns + si];
+        co[((size_t)b * 3 + c) * K + r] = tgt[((size_t)b * 3 + c) * Nt + ti];
+    }
+}
+
+__global__ void add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 x = a[i], y = b[i];
+    o[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+
+}  // namespace
+
+// in [nb, R, C] (ld_in) -> out [nb, C, R] (ld_out)
+VCR_API int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, int ld_out,
+                          long long stride_in, long long stride_out, cudaStream_t stream) {
+    VCR_REQUIRE(in && out && nb > 0 && R > 0 && C > 0 && nb <= 65535);
+    dim3 g(vcr_cdiv(C, 32), vcr_cdiv(R, 32), nb), blk(32, 8);
+    transpose_kernel<<<g, blk, 0, stream>>>(in, out, R, C, ld_in, ld_out, stride_in, stride_out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_conv3_act(const float* xyz, const float* w, const float* bias, int B, int N, int Cout, float slope,
+                          float* out, int ldo, cudaStream_t stream) {
+    VCR_REQUIRE(xyz && w && bias && out && B > 0 && N > 0 && Cout > 0 && B <= 65535);
+    dim3 g(vcr_cdiv(N, 8), B), blk(32, 8);
+    conv3_kernel<<<g, blk, 0, stream>>>(xyz, w, bias, N, Cout, slope, out, ldo);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// out = a*(x-mean)/(std_unbiased+eps)+b (+ residual when residual != NULL)
+VCR_API int vcr_layernorm(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                          const float* residual, int ldr, float* out, int ldo, cudaStream_t stream) {
+    VCR_REQUIRE(x && a && b && out && M > 0);
+    if (D % 128 != 0 || D > 1024 || (ldx & 3) || (ldo & 3) || (residual && (ldr & 3))) return VCR_ERR_UNSUPPORTED;
+    const int wpb = 8;
+    dim3 g(vcr_cdiv(M, wpb));
+    switch (D / 128) {
+#define LN_CASE(V) case V: layernorm_kernel<V><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, residual, ldr, out, ldo); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+    }
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_softmax_rows(float* S, int ld, long long rows, int n, const uint8_t* keep, long long rows_per_batch,
+                             cudaStream_t stream) {
+    VCR_REQUIRE(S && rows > 0 && n > 0 && (!keep || rows_per_batch > 0));
+    softmax_rows_kernel<<<vcr_cdiv(rows, 8), 256, 0, stream>>>(S, ld, rows, n, keep, rows_per_batch);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API size_t vcr_colsum_workspace_bytes(int B, int n) { return (size_t)B * 32 * n * sizeof(float); }
+
+VCR_API int vcr_colsum(const float* P, int ld, int B, long long rows_per_batch, int n, float* out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+    VCR_REQUIRE(P && out && B > 0 && rows_per_batch > 0 && n > 0 && B <= 65535);
+    const int slabs = 32;
+    if (!workspace || workspace_bytes < vcr_colsum_workspace_bytes(B, n)) return VCR_ERR_WORKSPACE;
+    float* part = reinterpret_cast<float*>(workspace);
+    dim3 g(vcr_cdiv(n, 128), slabs, B);
+    colsum_partial_kernel<<<g, 128, 0, stream>>>(P, ld, rows_per_batch, n, slabs, part);
+    VCR_CHECK_LAUNCH();
+    dim3 g2(vcr_cdiv(n, 128), B);
+    colsum_final_kernel<<<g2, 128, 0, stream>>>(part, slabs, n, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_rowsum(const float* P, int ld, long long rows, int n, float* out, cudaStream_t stream) {
+    VCR_REQUIRE(P && out && rows > 0 && n > 0);
+    rowsum_kernel<<<vcr_cdiv(rows, 8), 256, 0, stream>>>(P, ld, rows, n, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_sqnorm_rows(const float* X, int ld, long long rows, int D, float* out, cudaStream_t stream) {
+    VCR_REQUIRE(X && out && rows > 0 && D > 0);
+    if ((D & 3) || (ld & 3)) return VCR_ERR_UNSUPPORTED;
+    sqnorm_rows_kernel<<<vcr_cdiv(rows, 8), 256, 0, stream>>>(X, ld, rows, D, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// dot: [B, Ns, ld] holding s_i . t_j on entry (overwritten).  mode 0: corr out; 1: P in place;
+// 2: best_idx / best_val out.
+VCR_API int vcr_softcorr_rows(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
+                              const float* tgt, int mode, float* corr, int* best_idx, float* best_val,
+                              cudaStream_t stream) {
+    VCR_REQUIRE(dot && xx && yy && B > 0 && Ns > 0 && Nt > 0 && B <= 65535);
+    if (mode == 0) VCR_REQUIRE(tgt && corr);
+    if (mode == 2) VCR_REQUIRE(best_idx && best_val);
+    dim3 g(vcr_cdiv(Ns, 8), B);
+    softcorr_rows_kernel<<<g, 256, 0, stream>>>(dot, ld, Ns, Nt, xx, yy, tgt, mode, corr, best_idx, best_val);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
+                        cudaStream_t stream) {
+    VCR_REQUIRE(dot && xx && yy && B > 0 && Ns > 0 && Nt > 0 && Ns <= 65535 && B <= 65535);
+    dim3 g(vcr_cdiv(Nt, 256), Ns, B);
+    negdist_kernel<<<g, 256, 0, stream>>>(dot, ld, Ns, Nt, xx, yy);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// rowsum of the column-softmax of pd (workspace: 2*B*Nt floats)
+VCR_API int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+    VCR_REQUIRE(pd && out && B > 0 && Ns > 0 && Nt > 0 && B <= 65535);
+    if (!workspace || workspace_bytes < (size_t)2 * B * Nt * sizeof(float)) return VCR_ERR_WORKSPACE;
+    float* cmax = reinterpret_cast<float*>(workspace);
+    float* csum = cmax + (size_t)B * Nt;
+    dim3 g(vcr_cdiv(Nt, 64), B);
+    col_lse_kernel<<<g, 64, 0, stream>>>(pd, ld, Ns, Nt, cmax, csum);
+    VCR_CHECK_LAUNCH();
+    dim3 g2(vcr_cdiv(Ns, 8), B);
+    rowsum_colsoftmax_kernel<<<g2, 256, 0, stream>>>(pd, ld, Ns, Nt, cmax, csum, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_gather_rows(const float* in, int ld_in, int B, int Nin, const int* idx, int K, int C, float* out,
+                            int ld_out, cudaStream_t stream) {
+    VCR_REQUIRE(in && idx && out && B > 0 && K > 0 && C > 0 && B <= 65535);
+    if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return VCR_ERR_UNSUPPORTED;
+    dim3 g(vcr_cdiv(K, 8), B);
+    gather_rows_kernel<<<g, 256, 0, stream>>>(in, ld_in, Nin, idx, K, C, out, ld_out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_gather_cols(const float* in, int B, int C, int Nin, const int* idx, int K, float* out,
+                            cudaStream_t stream) {
+    VCR_REQUIRE(in && idx && out && B > 0 && K > 0 && C > 0 && B <= 65535);
+    dim3 g(vcr_cdiv(K, 128), B);
+    gather_cols_kernel<<<g, 128, 0, stream>>>(in, C, Nin, idx, K, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_copair_gather(const float* src, const float* tgt, int B, int Ns, int Nt, const int* keep,
+                              const int* best_idx, int K, float* src_out, float* corr_out, cudaStream_t stream) {
+    VCR_REQUIRE(src && tgt && keep && best_idx && src_out && corr_out && B > 0 && K > 0 && B <= 65535);
+    dim3 g(vcr_cdiv(K, 128), B);
+    copair_gather_kernel<<<g, 128, 0, stream>>>(src, tgt, Ns, Nt, keep, best_idx, K, src_out, corr_out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream) {
+    VCR_REQUIRE(a && b && out && n > 0 && (n & 3) == 0);
+    add_kernel<<<vcr_cdiv(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(a),
+                                                        reinterpret_cast<const float4*>(b),
+                                                        reinterpret_cast<float4*>(out), (size_t)(n / 4));
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}

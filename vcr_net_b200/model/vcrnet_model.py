@@ -1,0 +1,129 @@
+"""VCRNet assembly, VCP head, SVD head and the --iter loop with the reference's API
+(reference model/vcrnet_model.py:21-43, 162-399, 463-518).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .. import ops
+from .lpdnet_model import LPDNet
+from .transformer import Transformer
+
+
+def vcrnetIter(net, src, tgt, iter=1):
+    """model/vcrnet_model.py:21-43: refine `iter` times, composing R_f <- R_i R_f, t_f <- R_i t_f + t_i."""
+    transformed_src = src
+    R_f = t_f = None
+    srcK = src_corrK = None
+    for _ in range(iter):
+        srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt)
+        transformed_src = ops.rigid_apply(transformed_src, R, t)
+        if R_f is None:
+            R_f, t_f = R.detach().clone(), t.detach().clone()
+        else:
+            ops.pose_compose_(R.detach(), t.detach(), R_f, t_f)
+    R_ba, t_ba = ops.pose_inverse(R_f, t_f)
+    return srcK, src_corrK, R_f, t_f, R_ba, t_ba
+
+
+class Identity(nn.Module):
+    def forward(self, *input):
+        return input
+
+
+class VcpTopK(nn.Module):
+    """model/vcrnet_model.py:162-347.  forward(src_emb, tgt_emb [B,D,N], src, tgt [B,3,N]) -> (src, src_corr)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.emb_nn = args.emb_nn
+        self.partial = args.partial
+        self.overlap2 = float(args.overlap2)
+
+    def forward_tokens(self, src_tok, tgt_tok, src, tgt):
+        if self.partial:
+            so, seo, to, teo, _, _ = Fn.vcp_select(src, src_tok, tgt, tgt_tok, self.overlap2)
+            s, c, _, _ = Fn.vcp_copair(so, seo, to, teo, self.overlap2)
+            return s, c
+        return src, Fn.vcp_whole(src_tok.contiguous(), tgt_tok.contiguous(), tgt)
+
+    def forward(self, *input):
+        src_tok = ops.transpose_batched(input[0])
+        tgt_tok = ops.transpose_batched(input[1])
+        return self.forward_tokens(src_tok, tgt_tok, input[2], input[3])
+
+    # reference method names, channel-major signatures
+    def getCopairALL(self, src, src_emb, tgt, tgt_emb):
+        return src, Fn.vcp_whole(ops.transpose_batched(src_emb), ops.transpose_batched(tgt_emb), tgt)
+
+    def selectCom(self, src, src_emb, tgt, tgt_emb, overlap2=0.75):
+        so, seo, to, teo, _, _ = Fn.vcp_select(src, ops.transpose_batched(src_emb), tgt,
+                                               ops.transpose_batched(tgt_emb), float(overlap2))
+        return so, ops.transpose_batched(seo), to, ops.transpose_batched(teo), None, None
+
+    def getCopair(self, src, src_emb, tgt, tgt_emb, overlap2):
+        s, c, _, _ = Fn.vcp_copair(src, ops.transpose_batched(src_emb), tgt, ops.transpose_batched(tgt_emb),
+                                   float(overlap2))
+        return s, c
+
+
+class SVDHead(nn.Module):
+    """model/vcrnet_model.py:350-399.  forward(src, src_corr [B,3,M]) -> (R [B,3,3], t [B,3])."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.reflect = nn.Parameter(torch.eye(3), requires_grad=False)
+        self.reflect[2, 2] = -1
+
+    def forward(self, src, src_corr):
+        R, t, _, _ = ops.svd_head(src, src_corr)
+        return R, t
+
+
+class VCRNet(nn.Module):
+    """model/vcrnet_model.py:463-518.  forward(src, tgt [B,3,N]) ->
+    (srcK, src_corrK, R_ab, t_ab, R_ba, t_ba)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.emb_dims = args.emb_dims
+        self.cycle = args.cycle
+        if args.emb_nn == 'lpdnet':
+            self.emb_nn = LPDNet(args)
+        else:
+            raise Exception('Not implemented')           # pointnet / dgcnn: SURVEY.md section 8(f)
+        if args.pointer == 'identity':
+            self.pointer = Identity()
+        elif args.pointer == 'transformer':
+            self.pointer = Transformer(args=args)
+        else:
+            self.pointer = None
+        if args.vcp_nn == 'topK':
+            self.head = VcpTopK(args=args)
+        else:
+            raise Exception("Not implemented")            # att / dist heads: SURVEY.md section 8(f)
+        self.svd = SVDHead(args=args)
+
+    def forward(self, *input, stages=None):
+        src, tgt = input[0].contiguous(), input[1].contiguous()
+        B = src.shape[0]
+        same = src.shape == tgt.shape
+        if same:                                           # both clouds through ONE batch of 2B
+            emb = self.emb_nn.forward_tokens(torch.cat([src, tgt], dim=0))
+            src_tok, tgt_tok = emb[:B], emb[B:]
+        else:
+            src_tok, tgt_tok = self.emb_nn.forward_tokens(src), self.emb_nn.forward_tokens(tgt)
+        if stages is not None:
+            stages.update(src_emb0=src_tok, tgt_emb0=tgt_tok)
+        if isinstance(self.pointer, Transformer):
+            src_tok, tgt_tok = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True)   # :503-505
+        if stages is not None:
+            stages.update(src_emb=src_tok, tgt_emb=tgt_tok)
+        srcK, src_corrK = self.head.forward_tokens(src_tok, tgt_tok, src, tgt)                  # :507
+        R_ab, t_ab, R_ba, t_ba = ops.svd_head(srcK, src_corrK)                                  # :509-516
+        if self.cycle:
+            srcK_ba, corrK_ba = self.head.forward_tokens(tgt_tok, src_tok, tgt, src)
+            R_ba, t_ba, _, _ = ops.svd_head(srcK_ba, corrK_ba)
+        return srcK, src_corrK, R_ab, t_ab, R_ba, t_ba

@@ -1,0 +1,414 @@
+"""Thin torch-tensor front-end over the C ABI (include/vcr_b200.h).
+
+PyTorch is plumbing here: device memory (torch.empty), the current CUDA stream and nothing
+else.  Every function launches hand-written sm_100a kernels from libvcr_b200.so on
+``torch.cuda.current_stream()`` of the tensor's device; CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ._lib import lib
+
+_F32 = torch.float32
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, dtype=_F32):
+    if not t.is_cuda:
+        raise RuntimeError(f"vcr_net_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"vcr_net_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _rows(t: torch.Tensor):
+    """2-D row-major view info of a tensor whose last dim is contiguous and whose leading dims
+    collapse to a single row stride: (rows, cols, ld)."""
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    cols = t.shape[-1]
+    ld = t.stride(-2) if t.dim() >= 2 else cols
+    rows = 1
+    for d in range(t.dim() - 1):
+        rows *= t.shape[d]
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):       # leading dims must be dense over ld
+        assert t.shape[d] == 1 or t.stride(d) == exp, "tensor rows are not uniformly strided"
+        exp *= t.shape[d]
+    return rows, cols, ld
+
+
+# --------------------------------------------------------------------------------------------------
+# kNN / graph / FPS
+# --------------------------------------------------------------------------------------------------
+
+def knn_topk(x: torch.Tensor, k: int, token_major: bool = False, want64: bool = False):
+    """x [B,D,N] (or [B,N,D] when token_major) -> idx int32 [B,N,k] (and int64 when want64)."""
+    _chk(x, "x")
+    x = x.contiguous()
+    if token_major:
+        B, N, D = x.shape
+    else:
+        B, D, N = x.shape
+    L = lib()
+    idx32 = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
+    idx64 = torch.empty((B, N, k), dtype=torch.int64, device=x.device) if want64 else None
+    ws_bytes = L.vcr_knn_workspace_bytes(B, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.check(L.vcr_knn_topk(x.data_ptr(), B, D, N, k, int(token_major), idx32.data_ptr(),
+                           idx64.data_ptr() if want64 else None, ws.data_ptr(), ws_bytes, _stream(x)),
+            "vcr_knn_topk")
+    return (idx32, idx64) if want64 else idx32
+
+
+def graph_feature(xt: torch.Tensor, idx: torch.Tensor):
+    """xt token-major [B,N,D], idx int32 [B,N,k] -> [B,2D,N,k] (reference layout)."""
+    _chk(xt, "xt"); _chk(idx, "idx", torch.int32)
+    xt, idx = xt.contiguous(), idx.contiguous()
+    B, N, D = xt.shape
+    k = idx.shape[2]
+    out = torch.empty((B, 2 * D, N, k), dtype=_F32, device=xt.device)
+    L = lib()
+    L.check(L.vcr_graph_feature(xt.data_ptr(), B, D, N, k, idx.data_ptr(), out.data_ptr(), _stream(xt)),
+            "vcr_graph_feature")
+    return out
+
+
+def fps(xyz: torch.Tensor, npoint: int, want64: bool = True):
+    _chk(xyz, "xyz")
+    xyz = xyz.contiguous()
+    B, C, N = xyz.shape
+    assert C == 3
+    dt = torch.int64 if want64 else torch.int32
+    out = torch.empty((B, npoint), dtype=dt, device=xyz.device)
+    L = lib()
+    L.check(L.vcr_fps(xyz.data_ptr(), B, N, npoint, None if want64 else out.data_ptr(),
+                      out.data_ptr() if want64 else None, _stream(xyz)), "vcr_fps")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------------
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None, act: int = 0,
+         slope: float = 0.0, alpha: float = 1.0):
+    """out[M,N] = act(alpha * a[M,K] @ w[N,K]^T + bias) + residual.  a/out/residual may be strided
+    row views (last dim contiguous)."""
+    _chk(a, "a"); _chk(w, "w")
+    M, K, lda = _rows(a)
+    N, K2, ldb = _rows(w)
+    assert K == K2, (K, K2)
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (N,), dtype=_F32, device=a.device)
+    Mo, No, ldc = _rows(out)
+    assert (Mo, No) == (M, N)
+    ldr = 0
+    if residual is not None:
+        Mr, Nr, ldr = _rows(residual)
+        assert (Mr, Nr) == (M, N)
+    L = lib()
+    L.check(L.vcr_gemm_f32(a.data_ptr(), lda, 0, 0, w.data_ptr(), ldb, 0, 0, 0,
+                           out.data_ptr(), ldc, 0, 0,
+                           bias.data_ptr() if bias is not None else None,
+                           residual.data_ptr() if residual is not None else None, ldr, 0, 0,
+                           M, N, K, 1, 1, float(alpha), int(act), float(slope), _stream(a)), "vcr_gemm_f32")
+    return out
+
+
+def bgemm(a, a_ld, a_so, a_si, b, b_ld, b_so, b_si, b_layout, c, c_ld, c_so, c_si, M, N, K, nbo, nbi,
+          alpha=1.0):
+    """Raw batched GEMM over base tensors + element strides (attention heads, per-pair scores)."""
+    L = lib()
+    L.check(L.vcr_gemm_f32(a.data_ptr(), a_ld, a_so, a_si, b.data_ptr(), b_ld, b_so, b_si, b_layout,
+                           c.data_ptr(), c_ld, c_so, c_si, None, None, 0, 0, 0,
+                           M, N, K, nbo, nbi, float(alpha), 0, 0.0, _stream(c)), "vcr_gemm_f32")
+    return c
+
+
+# --------------------------------------------------------------------------------------------------
+# LPDNet pieces
+# --------------------------------------------------------------------------------------------------
+
+def conv3_act(xyz: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, slope: float):
+    """xyz [B,3,N] -> token-major [B,N,Cout]."""
+    _chk(xyz, "xyz")
+    xyz = xyz.contiguous()
+    B, _, N = xyz.shape
+    Cout = w.shape[0]
+    out = torch.empty((B, N, Cout), dtype=_F32, device=xyz.device)
+    L = lib()
+    L.check(L.vcr_conv3_act(xyz.data_ptr(), w.data_ptr(), bias.data_ptr(), B, N, Cout, float(slope),
+                            out.data_ptr(), Cout, _stream(xyz)), "vcr_conv3_act")
+    return out
+
+
+def edgeconv_dg(pq: torch.Tensor, idx: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, slope: float,
+                x1: torch.Tensor, x2: torch.Tensor):
+    """pq [B,N,256], idx int32 [B,N,20]; writes x1, x2 (row views [B,N,128])."""
+    B, N, _ = pq.shape
+    _, _, ldpq = _rows(pq)
+    _, _, ld1 = _rows(x1)
+    _, _, ld2 = _rows(x2)
+    L = lib()
+    L.check(L.vcr_edgeconv_dg(pq.data_ptr(), ldpq, idx.data_ptr(), idx.shape[2], N, B * N, w2.data_ptr(),
+                              b2.data_ptr(), float(slope), x1.data_ptr(), ld1, x2.data_ptr(), ld2, _stream(pq)),
+            "vcr_edgeconv_dg")
+
+
+def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float, out: torch.Tensor):
+    """out[b,n,:] = act(max_k p[b, idx[b,n,k], :] + q[b,n,:]); p, q, out are [B,N,C] row views."""
+    B, N, C = p.shape
+    _, _, ldp = _rows(p)
+    _, _, ldq = _rows(q)
+    _, _, ldo = _rows(out)
+    L = lib()
+    L.check(L.vcr_gather_max(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), idx.shape[2], N, B * N, C,
+                             float(slope), out.data_ptr(), ldo, _stream(p)), "vcr_gather_max")
+
+
+# --------------------------------------------------------------------------------------------------
+# Transformer pieces
+# --------------------------------------------------------------------------------------------------
+
+def layernorm(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, residual=None, out=None):
+    _chk(x, "x")
+    M, D, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=_F32, device=x.device)
+    _, _, ldo = _rows(out)
+    ldr = 0
+    if residual is not None:
+        _, _, ldr = _rows(residual)
+    L = lib()
+    L.check(L.vcr_layernorm(x.data_ptr(), ldx, a.data_ptr(), b.data_ptr(), float(eps), M, D,
+                            residual.data_ptr() if residual is not None else None, ldr,
+                            out.data_ptr(), ldo, _stream(x)), "vcr_layernorm")
+    return out
+
+
+def softmax_rows_(S: torch.Tensor, keep: torch.Tensor | None = None, rows_per_batch: int = 0):
+    rows, n, ld = _rows(S)
+    L = lib()
+    L.check(L.vcr_softmax_rows(S.data_ptr(), ld, rows, n, keep.data_ptr() if keep is not None else None,
+                               rows_per_batch, _stream(S)), "vcr_softmax_rows")
+    return S
+
+
+def colsum(P: torch.Tensor, B: int, out=None):
+    """P [B*rows_per_batch, n] -> [B, n] column sums per batch."""
+    rows, n, ld = _rows(P)
+    if out is None:
+        out = torch.empty((B, n), dtype=_F32, device=P.device)
+    L = lib()
+    wsb = L.vcr_colsum_workspace_bytes(B, n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=P.device)
+    L.check(L.vcr_colsum(P.data_ptr(), ld, B, rows // B, n, out.data_ptr(), ws.data_ptr(), wsb, _stream(P)),
+            "vcr_colsum")
+    return out
+
+
+def topk_select(vals: torch.Tensor, K: int, want_idx=True, want_mask=False):
+    _chk(vals, "vals")
+    vals = vals.contiguous()
+    B, n = vals.shape
+    idx = torch.empty((B, K), dtype=torch.int32, device=vals.device) if want_idx else None
+    mask = torch.empty((B, n), dtype=torch.uint8, device=vals.device) if want_mask else None
+    L = lib()
+    L.check(L.vcr_topk_select(vals.data_ptr(), B, n, K, idx.data_ptr() if want_idx else None,
+                              mask.data_ptr() if want_mask else None, _stream(vals)), "vcr_topk_select")
+    return idx, mask
+
+
+def attention_f32(q, k, v, B, h, Nq, Nk, dk, scale, out, keep=None, colsum_out=False, max_ws_bytes=1 << 31):
+    """softmax(q k^T * scale) v per (batch, head) in fp32 (model/transformer.py:13-55).
+
+    q/k/v: (tensor, ld, batch_stride, head_stride) tuples addressing [B, h, N, dk] inside fused
+    projection buffers; out likewise.  Scores are materialised per chunk of batches (fp32 mode);
+    the tensor-core modes use the flash kernel instead.  ``keep`` uint8 [B,Nk] masks keys.
+    Returns the per-batch column sums of the probabilities when ``colsum_out``."""
+    qt, qld, qsb, qsh = q
+    kt, kld, ksb, ksh = k
+    vt, vld, vsb, vsh = v
+    ot, old, osb, osh = out
+    dev = qt.device
+    per_b = h * Nq * Nk * 4
+    cb = max(1, min(B, max_ws_bytes // per_b))
+    S = torch.empty((cb, h, Nq, Nk), dtype=_F32, device=dev)
+    csum = torch.empty((B, Nk), dtype=_F32, device=dev) if colsum_out else None
+    esz = 4
+    for b0 in range(0, B, cb):
+        nb = min(cb, B - b0)
+        off = lambda t, sb: t.data_ptr() + b0 * sb * esz
+        L = lib()
+        st = _stream(qt)
+        L.check(L.vcr_gemm_f32(off(qt, qsb), qld, qsb, qsh, off(kt, ksb), kld, ksb, ksh, 0,
+                               S.data_ptr(), Nk, h * Nq * Nk, Nq * Nk, None, None, 0, 0, 0,
+                               Nq, Nk, dk, nb, h, float(scale), 0, 0.0, st), "vcr_gemm_f32(QK)")
+        Sv = S[:nb].view(nb * h * Nq, Nk)
+        kp = keep[b0:b0 + nb] if keep is not None else None
+        softmax_rows_(Sv, kp, h * Nq)
+        if colsum_out:
+            colsum(Sv, nb, out=csum[b0:b0 + nb])
+        L.check(L.vcr_gemm_f32(S.data_ptr(), Nk, h * Nq * Nk, Nq * Nk, off(vt, vsb), vld, vsb, vsh, 1,
+                               off(ot, osb), old, osb, osh, None, None, 0, 0, 0,
+                               Nq, dk, Nk, nb, h, 1.0, 0, 0.0, st), "vcr_gemm_f32(PV)")
+    return csum
+
+
+# --------------------------------------------------------------------------------------------------
+# VCP head
+# --------------------------------------------------------------------------------------------------
+
+def sqnorm_rows(x: torch.Tensor):
+    rows, D, ld = _rows(x)
+    out = torch.empty(x.shape[:-1], dtype=_F32, device=x.device)
+    L = lib()
+    L.check(L.vcr_sqnorm_rows(x.data_ptr(), ld, rows, D, out.data_ptr(), _stream(x)), "vcr_sqnorm_rows")
+    return out
+
+
+def pair_dots(s_tok: torch.Tensor, t_tok: torch.Tensor):
+    """s_tok [B,Ns,D], t_tok [B,Nt,D] (contiguous) -> dot [B,Ns,ld] with ld = Nt rounded up to 4."""
+    B, Ns, D = s_tok.shape
+    Nt = t_tok.shape[1]
+    ld = (Nt + 3) // 4 * 4
+    dot = torch.empty((B, Ns, ld), dtype=_F32, device=s_tok.device)
+    bgemm(s_tok, D, Ns * D, 0, t_tok, D, Nt * D, 0, 0, dot, ld, Ns * ld, 0, Ns, Nt, D, B, 1)
+    return dot, ld
+
+
+def softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=None, mode=0):
+    B = dot.shape[0]
+    dev = dot.device
+    L = lib()
+    corr = best_i = best_v = None
+    if mode == 0:
+        corr = torch.empty((B, 3, Ns), dtype=_F32, device=dev)
+    elif mode == 2:
+        best_i = torch.empty((B, Ns), dtype=torch.int32, device=dev)
+        best_v = torch.empty((B, Ns), dtype=_F32, device=dev)
+    L.check(L.vcr_softcorr_rows(dot.data_ptr(), ld, B, Ns, Nt, xx.data_ptr(), yy.data_ptr(),
+                                tgt.data_ptr() if tgt is not None else None, mode,
+                                corr.data_ptr() if corr is not None else None,
+                                best_i.data_ptr() if best_i is not None else None,
+                                best_v.data_ptr() if best_v is not None else None, _stream(dot)),
+            "vcr_softcorr_rows")
+    return corr, best_i, best_v
+
+
+def negdist_(dot, ld, Ns, Nt, xx, yy):
+    B = dot.shape[0]
+    L = lib()
+    L.check(L.vcr_negdist(dot.data_ptr(), ld, B, Ns, Nt, xx.data_ptr(), yy.data_ptr(), _stream(dot)), "vcr_negdist")
+    return dot
+
+
+def rowsum_colsoftmax(pd, ld, Ns, Nt):
+    B = pd.shape[0]
+    out = torch.empty((B, Ns), dtype=_F32, device=pd.device)
+    ws = torch.empty(2 * B * Nt, dtype=_F32, device=pd.device)
+    L = lib()
+    L.check(L.vcr_rowsum_colsoftmax(pd.data_ptr(), ld, B, Ns, Nt, out.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                    _stream(pd)), "vcr_rowsum_colsoftmax")
+    return out
+
+
+def gather_rows(x_tok: torch.Tensor, idx: torch.Tensor):
+    """x_tok [B,N,C] -> [B,K,C] rows idx[b,:]."""
+    B, N, C = x_tok.shape
+    _, _, ld = _rows(x_tok)
+    K = idx.shape[1]
+    out = torch.empty((B, K, C), dtype=_F32, device=x_tok.device)
+    L = lib()
+    L.check(L.vcr_gather_rows(x_tok.data_ptr(), ld, B, N, idx.data_ptr(), K, C, out.data_ptr(), C, _stream(x_tok)),
+            "vcr_gather_rows")
+    return out
+
+
+def gather_cols(x: torch.Tensor, idx: torch.Tensor):
+    """x [B,C,N] channel-major -> [B,C,K]."""
+    x = x.contiguous()
+    B, C, N = x.shape
+    K = idx.shape[1]
+    out = torch.empty((B, C, K), dtype=_F32, device=x.device)
+    L = lib()
+    L.check(L.vcr_gather_cols(x.data_ptr(), B, C, N, idx.data_ptr(), K, out.data_ptr(), _stream(x)), "vcr_gather_cols")
+    return out
+
+
+def copair_gather(src_xyz, tgt_xyz, keep, best_i):
+    """src_k[b,:,r] = src[b,:,keep[b,r]];  corr_k[b,:,r] = tgt[b,:,best_i[b,keep[b,r]]]
+    (model/vcrnet_model.py:300-331 with tgtK == 1)."""
+    src_xyz, tgt_xyz = src_xyz.contiguous(), tgt_xyz.contiguous()
+    B, _, Ns = src_xyz.shape
+    Nt = tgt_xyz.shape[2]
+    K = keep.shape[1]
+    so = torch.empty((B, 3, K), dtype=_F32, device=src_xyz.device)
+    co = torch.empty((B, 3, K), dtype=_F32, device=src_xyz.device)
+    L = lib()
+    L.check(L.vcr_copair_gather(src_xyz.data_ptr(), tgt_xyz.data_ptr(), B, Ns, Nt, keep.data_ptr(),
+                                best_i.data_ptr(), K, so.data_ptr(), co.data_ptr(), _stream(src_xyz)),
+            "vcr_copair_gather")
+    return so, co
+
+
+# --------------------------------------------------------------------------------------------------
+# SVD head / pose algebra / layout
+# --------------------------------------------------------------------------------------------------
+
+def svd_head(src: torch.Tensor, corr: torch.Tensor, want_H=False):
+    _chk(src, "src"); _chk(corr, "src_corr")
+    src, corr = src.contiguous(), corr.contiguous()
+    B, _, M = src.shape
+    dev = src.device
+    R = torch.empty((B, 3, 3), dtype=_F32, device=dev)
+    t = torch.empty((B, 3), dtype=_F32, device=dev)
+    Rb = torch.empty((B, 3, 3), dtype=_F32, device=dev)
+    tb = torch.empty((B, 3), dtype=_F32, device=dev)
+    H = torch.empty((B, 3, 3), dtype=_F32, device=dev) if want_H else None
+    L = lib()
+    L.check(L.vcr_svd_head(src.data_ptr(), corr.data_ptr(), B, M, R.data_ptr(), t.data_ptr(), Rb.data_ptr(),
+                           tb.data_ptr(), H.data_ptr() if want_H else None, _stream(src)), "vcr_svd_head")
+    return (R, t, Rb, tb, H) if want_H else (R, t, Rb, tb)
+
+
+def rigid_apply(pc: torch.Tensor, R: torch.Tensor, t: torch.Tensor):
+    _chk(pc, "point_cloud")
+    pc, R, t = pc.contiguous(), R.contiguous(), t.contiguous()
+    B, _, N = pc.shape
+    out = torch.empty_like(pc)
+    L = lib()
+    L.check(L.vcr_rigid_apply(pc.data_ptr(), R.data_ptr(), t.data_ptr(), B, N, out.data_ptr(), _stream(pc)),
+            "vcr_rigid_apply")
+    return out
+
+
+def pose_compose_(R_i, t_i, R_f, t_f):
+    L = lib()
+    L.check(L.vcr_pose_compose(R_i.data_ptr(), t_i.data_ptr(), R_f.data_ptr(), t_f.data_ptr(), R_f.shape[0],
+                               _stream(R_f)), "vcr_pose_compose")
+
+
+def pose_inverse(R, t):
+    Ri, ti = torch.empty_like(R), torch.empty_like(t)
+    L = lib()
+    L.check(L.vcr_pose_inverse(R.data_ptr(), t.data_ptr(), Ri.data_ptr(), ti.data_ptr(), R.shape[0], _stream(R)),
+            "vcr_pose_inverse")
+    return Ri, ti
+
+
+def transpose_batched(x: torch.Tensor):
+    """[nb,R,C] contiguous -> [nb,C,R] contiguous (module-boundary layout change)."""
+    _chk(x, "x")
+    x = x.contiguous()
+    nb, R, C = x.shape
+    out = torch.empty((nb, C, R), dtype=_F32, device=x.device)
+    L = lib()
+    L.check(L.vcr_transpose(x.data_ptr(), out.data_ptr(), nb, R, C, C, R, R * C, R * C, _stream(x)), "vcr_transpose")
+    return out
