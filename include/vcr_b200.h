@@ -40,7 +40,7 @@ int vcr_abi_version(void);
 /* ---- kNN graph: util/util.py:143-160 knn(x,k) -------------------------------------------------
  * pd_ij = (-xx_j - (-2 x_i.x_j)) - xx_i, neighbours = ranks 1..k of the descending order (rank 0
  * dropped exactly like `topk(k+1)[..., 1:]`), ties -> lower index.  x: [B,D,N] (token_major=0) or
- * [B,N,D] (token_major=1); D in {3,64}; 1<=k<=31; idx32 / idx64: [B,N,k], either may be NULL. */
+ * [B,N,D] (token_major=1); any D (fast paths for 3 and 64); 1<=k<=31; idx32 / idx64: [B,N,k], either may be NULL. */
 size_t vcr_knn_workspace_bytes(int B, int N);
 int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
                  int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream);

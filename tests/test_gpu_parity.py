@@ -64,7 +64,8 @@ def test_knn_vs_live_reference_grid():
 
 @pytest.mark.parametrize("D,N,k,tm", [(3, 777, 20, False), (3, 33, 20, False), (64, 130, 20, True),
                                       (3, 1024, 1, False), (64, 300, 8, False), (3, 4096, 20, False),
-                                      (64, 2048, 20, True), (3, 21, 20, False)])
+                                      (64, 2048, 20, True), (3, 21, 20, False), (8, 200, 5, False),
+                                      (128, 515, 20, True), (6, 300, 20, False), (200, 64, 31, False)])
 def test_knn_shapes(D, N, k, tm):
     rs = np.random.RandomState(N + D)
     x = rs.randn(2, D, N).astype(np.float32)
@@ -88,7 +89,7 @@ def test_knn_errors():
     with pytest.raises(RuntimeError):
         V.knn(torch.zeros(1, 3, 64), 20)   # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
-        V.knn(torch.zeros(1, 5, 64, device=DEV), 20)   # unsupported D
+        V.knn(torch.zeros(1, 3, 64, device=DEV), 40)   # k > 31
 
 
 def test_graph_feature():
@@ -286,7 +287,7 @@ def test_svd_head_vs_golden(net_whole):
     Ro, to = O.svd_head(g["src"], g["corr"])
     assert np.abs(nump(R) - Ro).max() < 1e-5 and np.abs(nump(t) - to).max() < 1e-5
     # exact recovery of a known rigid motion, incl. a big batch (size-independent property)
-    p = synth.make_pairs(64, 300, first_item=100)
+    p = synth.make_pairs(64, 300, first_item=100, aligned=True)   # index-aligned => exact rigid motion
     R2, t2, Rb, tb = ops.svd_head(cu(p["src"]), cu(p["tgt"]))
     assert np.abs(nump(R2) - p["R_ab"]).max() < 1e-5 and np.abs(nump(t2) - p["t_ab"]).max() < 1e-5
     assert np.abs(nump(Rb) - p["R_ab"].transpose(0, 2, 1)).max() < 1e-5

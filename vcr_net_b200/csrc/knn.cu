@@ -226,12 +226,138 @@ int dispatch_ks(const float* x, const float* xx, int B, int N, int k, int32_t* i
     return VCR_ERR_UNSUPPORTED;
 }
 
+
+// Generic feature width (any D >= 1): same canonical arithmetic, the d-chain is walked in chunks of
+// GD_DC dims staged through shared memory (query chunk + candidate chunk); every thread keeps the
+// CPW running dot products of its warp's candidate slice in registers across chunks.
+constexpr int GD_DC = 32;
+
+template <int KS, bool TOKEN_MAJOR>
+__global__ void __launch_bounds__(QPB * NWARP)
+knn_generic_kernel(const float* __restrict__ x, const float* __restrict__ xx, int D, int N, int k,
+                   int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+    constexpr int DP = GD_DC + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;                      // [TJ][DP]
+    float* qs = tile + TJ * DP;              // [QPB][GD_DC + 1]
+    float* txx = qs + QPB * (GD_DC + 1);     // [TJ]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * QPB;
+    const int qi = q0 + lane;
+    const bool qvalid = qi < N;
+    const float* xb = x + (size_t)b * D * N;
+    const float* xxb = xx + (size_t)b * N;
+    const float xxq = qvalid ? xxb[qi] : 0.f;
+    TopList<KS> top;
+    top.init();
+    for (int j0 = 0; j0 < N; j0 += TJ) {
+        float acc[CPW];
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) acc[c] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += GD_DC) {
+            const int dc = min(GD_DC, D - d0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < TJ * GD_DC; e += blockDim.x) {
+                int j, d;
+                if (TOKEN_MAJOR) { j = e / GD_DC; d = e - j * GD_DC; } else { d = e / TJ; j = e - d * TJ; }
+                float v = 0.f;
+                if (d < dc && j0 + j < N)
+                    v = TOKEN_MAJOR ? xb[(size_t)(j0 + j) * D + d0 + d] : xb[(size_t)(d0 + d) * N + j0 + j];
+                tile[j * DP + d] = v;
+            }
+            for (int e = threadIdx.x; e < QPB * GD_DC; e += blockDim.x) {
+                int q, d;
+                if (TOKEN_MAJOR) { q = e / GD_DC; d = e - q * GD_DC; } else { d = e / QPB; q = e - d * QPB; }
+                float v = 0.f;
+                if (d < dc && q0 + q < N)
+                    v = TOKEN_MAJOR ? xb[(size_t)(q0 + q) * D + d0 + d] : xb[(size_t)(d0 + d) * N + q0 + q];
+                qs[q * (GD_DC + 1) + d] = v;
+            }
+            if (d0 == 0)
+                for (int j = threadIdx.x; j < TJ; j += blockDim.x) txx[j] = (j0 + j < N) ? xxb[j0 + j] : 0.f;
+            __syncthreads();
+            const float* qrow = qs + lane * (GD_DC + 1);
+            for (int d = 0; d < dc; ++d) {
+                const float qv = qrow[d];
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) acc[c] = fmaf(qv, tile[(warp * CPW + c) * DP + d], acc[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int jl = warp * CPW + c, jg = j0 + jl;
+            const float pd = __fsub_rn(__fsub_rn(-txx[jl], -2.f * acc[c]), xxq);
+            if (jg < N) top.push(pd, jg);
+        }
+    }
+    __syncthreads();
+    float* mv = smem;
+    int* mi = reinterpret_cast<int*>(smem + NWARP * QPB * KS);
+    if (warp > 0) {
+#pragma unroll
+        for (int p = 0; p < KS; ++p) {
+            mv[(warp * QPB + lane) * KS + p] = top.v[p];
+            mi[(warp * QPB + lane) * KS + p] = top.i[p];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < NWARP; ++w) {
+#pragma unroll 1
+            for (int p = 0; p < KS; ++p) {
+                const float v = mv[(w * QPB + lane) * KS + p];
+                const int i = mi[(w * QPB + lane) * KS + p];
+                if (i == 0x7fffffff) break;
+                top.push_lex(v, i);
+            }
+        }
+        if (qvalid) {
+            const size_t o = ((size_t)b * N + qi) * k;
+#pragma unroll
+            for (int p = 1; p < KS; ++p) {
+                if (p <= k) {
+                    if (idx32) idx32[o + p - 1] = top.i[p];
+                    if (idx64) idx64[o + p - 1] = (int64_t)top.i[p];
+                }
+            }
+        }
+    }
+}
+
+template <int KS, bool TM>
+int launch_knn_generic(const float* x, const float* xx, int B, int D, int N, int k, int32_t* i32, int64_t* i64,
+                       cudaStream_t st) {
+    size_t tile_bytes = (size_t)(TJ * (GD_DC + 4) + QPB * (GD_DC + 1) + TJ) * sizeof(float);
+    size_t merge_bytes = (size_t)NWARP * QPB * KS * 8;
+    size_t smem = tile_bytes > merge_bytes ? tile_bytes : merge_bytes;
+    auto kern = knn_generic_kernel<KS, TM>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return VCR_ERR_LAUNCH;
+    }
+    dim3 grid(vcr_cdiv(N, QPB), B);
+    kern<<<grid, QPB * NWARP, smem, st>>>(x, xx, D, N, k, i32, i64);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+template <bool TM>
+int dispatch_generic(const float* x, const float* xx, int B, int D, int N, int k, int32_t* i32, int64_t* i64,
+                     cudaStream_t st) {
+    if (k == 20) return launch_knn_generic<21, TM>(x, xx, B, D, N, k, i32, i64, st);
+    if (k <= 8) return launch_knn_generic<9, TM>(x, xx, B, D, N, k, i32, i64, st);
+    if (k <= 31) return launch_knn_generic<32, TM>(x, xx, B, D, N, k, i32, i64, st);
+    return VCR_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 VCR_API size_t vcr_knn_workspace_bytes(int B, int N) { return (size_t)B * N * sizeof(float); }
 
 // x: [B,D,N] (token_major=0, the reference layout) or [B,N,D] (token_major=1); idx: [B,N,k].
-// Either idx32 or idx64 (or both) may be given.  Requires 1 <= k <= 31, N >= k+1, D in {3, 64}.
+// Either idx32 or idx64 (or both) may be given.  Requires 1 <= k <= 31, N >= k+1; D = 3 and D = 64 take the
+// register-resident fast path, any other D the chunked generic kernel.
 VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
                          int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     VCR_REQUIRE(x && (idx32 || idx64) && B > 0 && N > 0 && k >= 1);
@@ -249,5 +375,6 @@ VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_m
         return token_major ? dispatch_ks<64, true>(x, xx, B, N, k, idx32, idx64, stream)
                            : dispatch_ks<64, false>(x, xx, B, N, k, idx32, idx64, stream);
     }
-    return VCR_ERR_UNSUPPORTED;
+    return token_major ? dispatch_generic<true>(x, xx, B, D, N, k, idx32, idx64, stream)
+                       : dispatch_generic<false>(x, xx, B, D, N, k, idx32, idx64, stream);
 }

@@ -8,6 +8,7 @@
 namespace {
 
 __device__ __forceinline__ unsigned int float_desc_key(float v) {
+    if (v == 0.f) v = 0.f;                               // -0.0 and +0.0 compare equal: one key
     unsigned int u = __float_as_uint(v);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // ascending order-preserving
     return ~u;                                           // descending
