@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--workload", default="whole", choices=["whole", "partial"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: config's)")
     ap.add_argument("--num-points", type=int, default=1024)
-    ap.add_argument("--precision", default=os.environ.get("VCR_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("VCR_PRECISION", "h3"),
+                    choices=["fp32", "h3", "fp16", "bf16"],
+                    help="matrix engine: fp32 SIMT | h3 = tcgen05 3-term fp16 split (fp32 parity) | fp16 | bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=2)
     return ap.parse_args()
@@ -173,6 +175,8 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from vcr_net_b200 import config as vcfg
+    vcfg.set_precision(a.precision)
     L = lib()
     ckpt = load_ckpt()
     net = V.VCRNet(default_args(partial=cfg["partial"], overlap2=cfg["overlap2"])).to(dev).eval()
@@ -275,7 +279,7 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     for name, ms, args in prof:
         d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
         d["ms"] += ms; d["n"] += 1
-        if name == "vcr_gemm_f32":
+        if name in ("vcr_gemm_f32", "vcr_gemm_tc"):
             d["flops"] += gemm_flops(args)
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     peaks = {}
@@ -291,7 +295,9 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         ach = top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
-                    note="fp32 SIMT FFMA kernel measured against the dense bf16 tensor peak")
+                    note=("fp32 SIMT FFMA kernel measured against the dense bf16 tensor peak" if top[0] == "vcr_gemm_f32"
+                          else "algorithmic 2MNK flops; the h3 parity mode spends 3 fp16 tensor passes per product"
+                          if a.precision == "h3" else "single tensor pass"))
     else:
         roof.update(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs", 6650.0), unit="GB/s", frac=None)
     breakdown = {k: round(v["ms"] / nprof, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
@@ -299,7 +305,9 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     line = {
         "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": {"fp32": "f32", "h3": "f16x3-split+f32acc (fp32-equivalent)", "fp16": "f16", "bf16": "bf16"}[a.precision],
+        "data": "synthetic",
         "config": {"workload": cfg["name"], "batch_per_gpu": B, "num_points": a.num_points, "points_in_net": M,
                    "iter": cfg["iters"], "precision": a.precision, "parallelism": f"batch-shard x{world}, no collective",
                    "l2": "flushed between timed steps (256 MB fill)", "weights": "synthetic 59-key checkpoint"},

@@ -67,6 +67,28 @@ int vcr_gemm_f32(const float* A, int lda, long long sAo, long long sAi,
                  int M, int N, int K, int nb_outer, int nb_inner,
                  float alpha, int act, float slope, cudaStream_t stream);
 
+/* ---- tensor-core GEMM (tcgen05 + TMEM + TMA) --------------------------------------------------------
+ * Same call sites as vcr_gemm_f32, on "operand-format" inputs: 16-bit K-major buffers laid out
+ * [planes][rows][ld]; plane 0 = hi = fp16(x), plane 1 = lo = fp16((x-hi)*2^11) (mode 0, the fp32-parity
+ * 3-term split); modes 1 / 2 = single-plane fp16 / bf16 (throughput modes).  Per batch z = (zo, zi) the A rows
+ * start at zo*a_row_o + zi*a_row_i and the K range at column zo*a_col_o + zi*a_col_i (same for B), which
+ * addresses attention heads inside fused projection buffers without copies.  Outputs, each optional:
+ * C fp32 (+ residual R); H operand-format row-major for columns < h_split; HT operand-format transposed
+ * ([plane][col - h_split][row]) for columns >= h_split.  vcr_to_operand converts fp32 -> operand format. */
+int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_cols_total, long long a_plane,
+                long long a_row_o, long long a_row_i, int a_col_o, int a_col_i,
+                const void* B, int ldb, long long b_rows_total, int b_cols_total, long long b_plane,
+                long long b_row_o, long long b_row_i, int b_col_o, int b_col_i,
+                int M, int N, int K, int nb_outer, int nb_inner, int mode,
+                float alpha, const float* bias, int act, float slope,
+                float* C, int ldc, long long c_so, long long c_si,
+                const float* R, int ldr, long long r_so, long long r_si,
+                void* H, int ldh, long long h_plane, long long h_so, long long h_si, int h_split,
+                void* HT, int ldt, long long t_plane, long long t_so, long long t_si,
+                int out_planes, cudaStream_t stream);
+int vcr_to_operand(const float* x, int ld, long long rows, int cols, void* out, int ldo, long long plane_stride,
+                   int planes, int bf16, cudaStream_t stream);
+
 /* ---- LPDNet pieces: model/lpdnet_model.py:103-137 ------------------------------------------------
  * conv1_lpd (:111): xyz [B,3,N] -> token-major out[B*N, ldo] = LeakyReLU(W[Cout,3] p + bias). */
 int vcr_conv3_act(const float* xyz, const float* w, const float* bias, int B, int N, int Cout, float slope,
@@ -91,6 +113,18 @@ int vcr_softmax_rows(float* S, int ld, long long rows, int n, const uint8_t* kee
 size_t vcr_colsum_workspace_bytes(int B, int n);
 int vcr_colsum(const float* P, int ld, int B, long long rows_per_batch, int n, float* out, void* workspace,
                size_t workspace_bytes, cudaStream_t stream);
+/* operand-format producers for vcr_gemm_tc: LayerNorm output / softmax probabilities written directly as
+ * 16-bit hi(/lo) planes; row log-sum-exp statistics and the column sums of softmax(S) without
+ * materialising the probabilities (partial-overlap key selection, model/transformer.py:39). */
+int vcr_layernorm_operand(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                          void* out, int ldo, long long plane_stride, int planes, int bf16, cudaStream_t stream);
+int vcr_row_lse(const float* S, int ld, long long rows, int n, const uint8_t* keep, long long rows_per_batch,
+                float* rmax, float* rsum, cudaStream_t stream);
+int vcr_softmax_operand(const float* S, int ld, long long rows, int n, const uint8_t* keep,
+                        long long rows_per_batch, void* out, int ldo, long long plane_stride, int planes,
+                        int bf16, cudaStream_t stream);
+int vcr_colsum_softmax(const float* S, int ld, int B, long long rows_per_batch, int n, const float* rmax,
+                       const float* rsum, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int vcr_rowsum(const float* P, int ld, long long rows, int n, float* out, cudaStream_t stream);
 /* top-K (value desc, ties -> lower index): sorted indices and/or a uint8 membership mask (:41-47). */
 int vcr_topk_select(const float* vals, int B, int n, int K, int* idx_out, uint8_t* mask_out, cudaStream_t stream);

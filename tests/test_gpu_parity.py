@@ -31,6 +31,16 @@ def nump(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.fixture(params=["fp32", "h3"])
+def precision(request):
+    """Both fp32-parity engines: FP32 SIMT GEMMs and the tcgen05 3-term fp16-split GEMMs."""
+    from vcr_net_b200 import config
+    old = config.precision
+    config.set_precision(request.param)
+    yield request.param
+    config.set_precision(old)
+
+
 @pytest.fixture(scope="module")
 def net_whole(ckpt):
     net = V.VCRNet(default_args()).to(DEV).eval()
@@ -218,7 +228,7 @@ def test_attention_vs_golden():
 
 
 # ---------------------------------------------------------------- LPDNet ------------------------------
-def test_lpdnet_vs_golden(net_whole):
+def test_lpdnet_vs_golden(net_whole, precision):
     g = load_golden("lpdnet")
     emb = net_whole.emb_nn
     x = cu(g["x"])
@@ -238,7 +248,7 @@ def test_lpdnet_vs_golden(net_whole):
     assert np.array_equal(nump(y), nump(out_free).transpose(0, 2, 1))
 
 
-def test_lpdnet_slope02():
+def test_lpdnet_slope02(precision):
     g = load_golden("lpdnet")
     lpd = load_golden("lpd_pretrained_weights")
     m = V.LPDNet(default_args(), negative_slope=0.2).to(DEV).eval()
@@ -249,7 +259,7 @@ def test_lpdnet_slope02():
 
 
 # ---------------------------------------------------------------- Transformer -------------------------
-def test_transformer_vs_golden(net_whole, net_partial):
+def test_transformer_vs_golden(net_whole, net_partial, precision):
     g = load_golden("transformer")
     sp, tp = net_whole.pointer(cu(g["src_emb"]), cu(g["tgt_emb"]))
     assert rel_err(nump(sp), g["src_p"]) < TOL and rel_err(nump(tp), g["tgt_p"]) < TOL
@@ -265,7 +275,7 @@ def _col_set_diff(a, b):
     return n
 
 
-def test_vcp_head_vs_golden(net_whole, net_partial):
+def test_vcp_head_vs_golden(net_whole, net_partial, precision):
     g = load_golden("vcp_head")
     ov2 = float(g["overlap2"])
     s, c = net_whole.head(cu(g["src_emb"]), cu(g["tgt_emb"]), cu(g["src"]), cu(g["tgt"]))
@@ -306,7 +316,7 @@ def test_pose_algebra():
 
 
 # ---------------------------------------------------------------- full network ------------------------
-def test_vcrnet_whole_vs_golden(net_whole):
+def test_vcrnet_whole_vs_golden(net_whole, precision):
     g = load_golden("vcrnet_whole")
     with torch.no_grad():
         out = V.vcrnetIter(net_whole, cu(g["src"]), cu(g["tgt"]), iter=1)
@@ -319,7 +329,7 @@ def test_vcrnet_whole_vs_golden(net_whole):
     assert rel_err(nump(out2[2]), g2["R_ab"]) < 5e-4 and rel_err(nump(out2[3]), g2["t_ab"]) < 5e-4
 
 
-def test_vcrnet_whole_vs_oracle_seeded(net_whole, ckpt):
+def test_vcrnet_whole_vs_oracle_seeded(net_whole, ckpt, precision):
     p = synth.make_pairs(2, 384, first_item=60)
     out = V.vcrnetIter(net_whole, cu(p["src"]), cu(p["tgt"]), iter=1)
     want = O.vcrnet_iter(ckpt, p["src"], p["tgt"], 1)
@@ -327,7 +337,7 @@ def test_vcrnet_whole_vs_oracle_seeded(net_whole, ckpt):
         assert rel_err(nump(o), w) < 5e-4, n
 
 
-def test_vcrnet_partial_vs_golden(net_partial):
+def test_vcrnet_partial_vs_golden(net_partial, precision):
     g = load_golden("vcrnet_partial")
     out1 = V.vcrnetIter(net_partial, cu(g["src"]), cu(g["tgt"]), iter=1)
     assert tuple(out1[0].shape) == g["srcK1"].shape
@@ -340,7 +350,7 @@ def test_vcrnet_partial_vs_golden(net_partial):
     assert np.allclose(np.linalg.det(R), 1.0, atol=1e-5)
 
 
-def test_full_size_properties(net_whole):
+def test_full_size_properties(net_whole, precision):
     """BASELINE cfg 1 size (B=16, N=1024): size-independent properties instead of an oracle run."""
     p = synth.make_pairs(16, 1024, first_item=200)
     src, tgt = cu(p["src"]), cu(p["tgt"])
@@ -360,3 +370,63 @@ def test_full_size_properties(net_whole):
     perm = torch.randperm(1024, device=DEV)
     outp = V.vcrnetIter(net_whole, src[:2][:, :, perm], tgt[:2], iter=1)
     assert np.abs(nump(outp[2]) - nump(out[2])[:2]).max() < 5e-4
+
+
+# ---------------------------------------------------------------- tensor-core GEMM --------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 520, 200), (4096, 1536, 512), (300, 64, 1024)])
+def test_gemm_tc_h3_matches_fp64(M, N, K):
+    rs = np.random.RandomState(M + N)
+    a = rs.randn(M, K).astype(np.float32)
+    w = (rs.randn(N, K) * 0.05).astype(np.float32)
+    b = rs.randn(N).astype(np.float32)
+    r = rs.randn(M, N).astype(np.float32)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    c = torch.empty(M, N, device=DEV)
+    ops.gemm_tc(ops.to_operand(cu(a), "h3"), ops.to_operand(cu(w), "h3"), M, N, K, c=c)
+    assert rel_err(nump(c), ref) < 3e-6                    # fp32-level (SIMT fp32 gives ~1e-6 here)
+    h = ops.Operand.empty(M, N, "h3", DEV)
+    ops.gemm_tc(ops.to_operand(cu(a), "h3"), ops.to_operand(cu(w), "h3"), M, N, K, bias=cu(b), act=1, slope=0.2,
+                alpha=0.5, c=c, residual=cu(r), h=h, h_split=N)
+    z = 0.5 * ref + b
+    z = np.where(z >= 0, z, 0.2 * z)
+    assert rel_err(nump(c), z + r) < 3e-6
+    assert rel_err(nump(h.to_float()), z + r) < 3e-6       # operand-format output carries hi + lo/2^11
+    for mode, tol in (("fp16", 2e-3), ("bf16", 2e-2)):
+        ops.gemm_tc(ops.to_operand(cu(a), mode), ops.to_operand(cu(w), mode), M, N, K, c=c)
+        assert rel_err(nump(c), ref) < tol
+
+
+def test_gemm_tc_batched_heads_and_transposed_output():
+    rs = np.random.RandomState(1)
+    B, h, N, dk = 2, 4, 256, 128
+    D = h * dk
+    x = rs.randn(B * N, D).astype(np.float32)
+    w = (rs.randn(3 * D, D) * 0.05).astype(np.float32)
+    qkv_ref = x.astype(np.float64) @ w.astype(np.float64).T
+    qk = ops.Operand.empty(B * N, 2 * D, "h3", DEV)
+    vt = ops.Operand.empty(B * D, N, "h3", DEV)
+    ops.gemm_tc(ops.to_operand(cu(x), "h3"), ops.to_operand(cu(w), "h3"), N, 3 * D, D, nbo=B, a_off=(N, 0, 0, 0),
+                h=qk, h_strides=(N * qk.ld, 0), h_split=2 * D, ht=vt, ht_strides=(D * vt.ld, 0))
+    assert rel_err(nump(qk.to_float()), qkv_ref[:, :2 * D]) < 3e-6
+    v_ref = qkv_ref[:, 2 * D:].reshape(B, N, D).transpose(0, 2, 1).reshape(B * D, N)
+    assert rel_err(nump(vt.to_float()), v_ref) < 3e-6
+    S = torch.empty(B, h, N, N, device=DEV)
+    ops.gemm_tc(qk.cols_view(0, D), qk.cols_view(D, D), N, N, dk, nbo=B, nbi=h, a_off=(N, 0, 0, dk),
+                b_off=(N, 0, 0, dk), alpha=0.25, c=S, c_strides=(h * N * N, N * N))
+    q = qkv_ref[:, :D].reshape(B, N, h, dk).transpose(0, 2, 1, 3)
+    k = qkv_ref[:, D:2 * D].reshape(B, N, h, dk).transpose(0, 2, 1, 3)
+    assert rel_err(nump(S), 0.25 * q @ k.transpose(0, 1, 3, 2)) < 3e-6
+
+
+@pytest.mark.parametrize("mode,tol", [("fp16", 3e-3), ("bf16", 3e-2)])
+def test_throughput_modes_reported_tolerance(net_whole, mode, tol):
+    """Single-pass tensor-core modes: NOT parity modes; their measured tolerance is recorded here."""
+    from vcr_net_b200 import config
+    g = load_golden("transformer")
+    old = config.precision
+    config.set_precision(mode)
+    try:
+        sp, tp = net_whole.pointer(cu(g["src_emb"]), cu(g["tgt_emb"]))
+    finally:
+        config.set_precision(old)
+    assert rel_err(nump(sp), g["src_p"]) < tol and rel_err(nump(tp), g["tgt_p"]) < tol

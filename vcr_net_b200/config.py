@@ -1,0 +1,19 @@
+"""Run-time precision policy of the matrix engine.
+
+  "fp32"  hand-written FP32 SIMT GEMMs everywhere (reference-exact arithmetic type)
+  "h3"    tcgen05 tensor cores with 3-term fp16 split operands: fp32-level accuracy (the parity mode
+          on tensor cores)
+  "fp16" / "bf16"  single-pass tensor-core throughput modes (reported separately with their tolerance)
+kNN / FPS / top-K selections and the SVD head always run in exact fp32 / fp64 arithmetic.
+"""
+import os
+
+precision = os.environ.get("VCR_PRECISION", "h3")
+VALID = ("fp32", "h3", "fp16", "bf16")
+
+
+def set_precision(p: str):
+    global precision
+    if p not in VALID:
+        raise ValueError(f"precision must be one of {VALID}")
+    precision = p

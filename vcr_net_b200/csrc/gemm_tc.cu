@@ -1,0 +1,412 @@
+// tcgen05 / TMEM / TMA GEMM: the tensor-core matrix engine of the path (sm_100a only).
+//
+//   C[z] = epilogue( alpha * A[z] (M x K) * B[z]^T (N x K) ),  both operands K-major 16-bit,
+//   fed by TMA (128-byte swizzle) into a multi-stage shared-memory ring, multiplied by
+//   tcgen05.mma (cta_group::1, 128 x 128 x 16 per instruction) into TMEM accumulators that are
+//   double-buffered so the epilogue of tile i overlaps the main loop of tile i+1 (persistent CTAs,
+//   one per SM, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+//   warps 4-7 epilogue).
+//
+// Precision modes:
+//   NTERMS = 3, fp16 "split" operands ("h3", the fp32-parity mode): every fp32 value x is carried as
+//       hi = fp16(x), lo = fp16((x - hi) * 2^11)  (two planes of the operand buffer), and
+//       x*y ~= hi*hi' + 2^-11 (hi*lo' + lo*hi') with the main term and the correction term in SEPARATE
+//       TMEM accumulators (D0, D1), combined in fp32 in the epilogue: ~2^-22 relative error per product,
+//       3 tensor-core passes at the fp16 rate (a tf32 x3 scheme would cost 3 passes at HALF that rate).
+//   NTERMS = 1: plain fp16 or bf16 operands (throughput modes, reported separately).
+//
+// Epilogue (fused, straight from TMEM): alpha, + bias[n], LeakyReLU, + residual, then any of
+//   - fp32 row-major C,
+//   - operand-format ("H2": [plane][row][ld] fp16 hi/lo) row-major output for columns < h_split,
+//   - operand-format TRANSPOSED output for columns >= h_split (V^T for attention: with one TMEM lane
+//     = one row per thread the transposed store is the coalesced one).
+// so consecutive GEMMs never round-trip through a separate conversion kernel.
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int TILE_BYTES = 128 * 128;       // 128 rows x 128 B
+
+struct TcGemmParams {
+    int M, N, K;
+    int nb_outer, nb_inner;
+    long long a_row_o, a_row_i; int a_col_o, a_col_i;
+    long long b_row_o, b_row_i; int b_col_o, b_col_i;
+    float alpha; const float* bias; int act; float slope;
+    float* C; int ldc; long long c_so, c_si;
+    const float* R; int ldr; long long r_so, r_si;
+    __half* H; int ldh; long long h_plane, h_so, h_si; int h_split;
+    __half* HT; int ldt; long long t_plane, t_so, t_si;
+    int out_planes;      // 2: write hi and lo planes, 1: hi only
+    int out_bf16;        // operand-format outputs are bf16 instead of fp16 (bf16 throughput mode)
+    int debug;           // timing probes (VCR_TC_DEBUG): 1 = skip global stores, 2 = skip smem staging too
+};
+
+template <int NTERMS>
+struct Cfg {
+    static constexpr int PLANES = NTERMS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = 2 * PLANES * TILE_BYTES;
+    static constexpr int NSTAGES = NTERMS == 3 ? 3 : 6;
+    static constexpr int ACC_COLS = NTERMS == 3 ? 2 * BN : BN;      // D0 | D1
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;                  // double-buffered
+    static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      4 * 32 * 32 * 4 /*epilogue transpose staging*/;
+};
+
+using tc::pack_h2;
+using tc::lo_part;
+
+template <int NTERMS, int FMT>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+    using C_ = Cfg<NTERMS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::NSTAGES * C_::STAGE_BYTES);
+    uint64_t* full = bars;                         // [NSTAGES]
+    uint64_t* empty = bars + C_::NSTAGES;          // [NSTAGES]
+    uint64_t* tfull = bars + 2 * C_::NSTAGES;      // [2]
+    uint64_t* tempty = tfull + 2;                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* stage_buf = reinterpret_cast<float*>(smem + C_::NSTAGES * C_::STAGE_BYTES + 256);   // [4 warps][32][32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_per_z = tiles_m * tiles_n;
+    const long long total_tiles = (long long)tiles_per_z * p.nb_outer * p.nb_inner;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C_::NSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, C_::TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (tc::elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
+                const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+                const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
+                const int a_row = (int)(zo * p.a_row_o + zi * p.a_row_i) + m_blk * BM;
+                const int b_row = (int)(zo * p.b_row_o + zi * p.b_row_i) + n_blk * BN;
+                const int a_col = zo * p.a_col_o + zi * p.a_col_i;
+                const int b_col = zo * p.b_col_o + zi * p.b_col_i;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+                    uint8_t* st = smem + s * C_::STAGE_BYTES;
+#pragma unroll
+                    for (int pl = 0; pl < C_::PLANES; ++pl) {
+                        tc::tma_load_3d(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
+                        tc::tma_load_3d(st + (C_::PLANES + pl) * TILE_BYTES, &tmB, &full[s], b_col + kb * BK, b_row, pl);
+                    }
+                    if (++s == C_::NSTAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc(BM, BN, FMT);
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int a = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                tc::mbar_wait(&tempty[a], aph ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d0 = tmem_base + a * C_::ACC_COLS;
+                const uint32_t d1 = d0 + BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + s * C_::STAGE_BYTES);
+                    const uint64_t a_hi = tc::umma_desc_k_sw128(st);
+                    const uint64_t b_hi = tc::umma_desc_k_sw128(st + C_::PLANES * TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint32_t acc = (kb | kk) != 0;
+                        const uint64_t adv = (uint64_t)(kk * 32 >> 4);      // 16 elements = 32 B along K
+                        tc::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
+                        if (NTERMS == 3) {
+                            const uint64_t a_lo = tc::umma_desc_k_sw128(st + TILE_BYTES);
+                            const uint64_t b_lo = tc::umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                            tc::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                            tc::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1);
+                        }
+                    }
+                    tc::umma_commit(&empty[s]);               // smem slot free once these MMAs retire
+                    if (++s == C_::NSTAGES) { s = 0; ph ^= 1; }
+                }
+                tc::umma_commit(&tfull[a]);                    // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int ew = warp - 4;                               // == warp % 4: TMEM lane quarter
+        int it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
+            const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+            const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            tc::mbar_wait(&tfull[a], aph);
+            tc::tc_fence_after();
+            const int row = m_blk * BM + ew * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t tadr = tmem_base + a * C_::ACC_COLS + ((uint32_t)(ew * 32) << 16);
+            float* Cz = p.C ? p.C + zo * p.c_so + zi * p.c_si : nullptr;
+            const float* Rz = p.R ? p.R + zo * p.r_so + zi * p.r_si : nullptr;
+            __half* Hz = p.H ? p.H + zo * p.h_so + zi * p.h_si : nullptr;
+            __half* Tz = p.HT ? p.HT + zo * p.t_so + zi * p.t_si : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = n_blk * BN + c0;
+                if (col0 >= p.N) break;                        // warp-uniform
+                uint32_t r0[32];
+                float v[32];
+                tc::tmem_ld_32x32(tadr + c0, r0);
+                if (NTERMS == 3) {
+                    uint32_t r1[32];
+                    tc::tmem_ld_32x32(tadr + BN + c0, r1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), 1.f / 2048.f, __uint_as_float(r0[j]));
+                } else {
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+                }
+                const bool full_chunk = col0 + 32 <= p.N;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t2 = p.alpha * v[j];
+                    if (p.bias && col0 + j < p.N) t2 += p.bias[col0 + j];
+                    if (p.act == 1) t2 = leaky(t2, p.slope);
+                    v[j] = t2;
+                }
+                if (Tz && row_ok && col0 + 32 > p.h_split) {
+                    // operand-format transposed: HT[plane][col - h_split][row]; lanes = consecutive rows,
+                    // so this direct store from the one-row-per-thread TMEM layout is already coalesced
+                    for (int pl = 0; pl < p.out_planes; ++pl) {
+                        unsigned short* tt = reinterpret_cast<unsigned short*>(Tz + pl * p.t_plane);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            if (col < p.N && col >= p.h_split) {
+                                const float x = pl == 0 ? v[j] : lo_part(v[j], p.out_bf16);
+                                const uint32_t w = pack_h2(x, 0.f, p.out_bf16);
+                                tt[(size_t)(col - p.h_split) * p.ldt + row] = (unsigned short)(w & 0xffff);
+                            }
+                        }
+                    }
+                }
+                const bool want_rm = (Cz != nullptr) || (Hz && col0 < p.h_split);
+                if (!want_rm || p.debug == 2) continue;                         // warp-uniform
+                // ---- row-major outputs: transpose through a swizzled smem tile so that every global
+                //      access of the warp covers whole 128-byte rows (4 rows x 128 B per instruction) ----
+                float* stg = stage_buf + ew * (32 * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
+                        make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                const int c4 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int rl = itr * 4 + rsub;
+                    const int grow = m_blk * BM + ew * 32 + rl;
+                    float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+                    const int col = col0 + c4 * 4;
+                    if (grow >= p.M || col >= p.N) continue;
+                    const bool vec = col + 4 <= p.N;
+                    if (Rz) {
+                        const float* rr = Rz + (size_t)grow * p.ldr + col;
+                        if (vec && (p.ldr & 3) == 0) {
+                            const float4 q = *reinterpret_cast<const float4*>(rr);
+                            x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                        } else {
+                            x.x += rr[0];
+                            if (col + 1 < p.N) x.y += rr[1];
+                            if (col + 2 < p.N) x.z += rr[2];
+                            if (col + 3 < p.N) x.w += rr[3];
+                        }
+                    }
+                    if (p.debug == 1) { if (x.x == 123.456f) Cz[0] = x.y; continue; }
+                    if (Cz) {
+                        float* cc = Cz + (size_t)grow * p.ldc + col;
+                        if (vec && (p.ldc & 3) == 0) {
+                            *reinterpret_cast<float4*>(cc) = x;
+                        } else {
+                            cc[0] = x.x;
+                            if (col + 1 < p.N) cc[1] = x.y;
+                            if (col + 2 < p.N) cc[2] = x.z;
+                            if (col + 3 < p.N) cc[3] = x.w;
+                        }
+                    }
+                    if (Hz && col < p.h_split) {
+                        for (int pl = 0; pl < p.out_planes; ++pl) {
+                            __half* hh = Hz + pl * p.h_plane + (size_t)grow * p.ldh + col;
+                            const float y0 = pl == 0 ? x.x : lo_part(x.x, p.out_bf16);
+                            const float y1 = pl == 0 ? x.y : lo_part(x.y, p.out_bf16);
+                            const float y2 = pl == 0 ? x.z : lo_part(x.z, p.out_bf16);
+                            const float y3 = pl == 0 ? x.w : lo_part(x.w, p.out_bf16);
+                            if (vec && col + 4 <= p.h_split && (p.ldh & 3) == 0) {
+                                *reinterpret_cast<uint2*>(hh) = make_uint2(pack_h2(y0, y1, p.out_bf16), pack_h2(y2, y3, p.out_bf16));
+                            } else {
+                                const float ys[4] = {y0, y1, y2, y3};
+                                for (int q = 0; q < 4; ++q)
+                                    if (col + q < p.N && col + q < p.h_split)
+                                        reinterpret_cast<unsigned short*>(hh)[q] =
+                                            (unsigned short)(pack_h2(ys[q], 0.f, p.out_bf16) & 0xffff);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty[a]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+}
+
+// fp32 [rows, cols] (ld) -> operand format planes (hi, and lo*2^11 when planes == 2)
+__global__ void to_operand_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
+                                  __half* __restrict__ out, int ldo, long long plane, int planes, int bf16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = cols >> 2;
+    if (i >= rows * c4) return;
+    const long long r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    uint2 w;
+    w.x = pack_h2(v.x, v.y, bf16); w.y = pack_h2(v.z, v.w, bf16);
+    *reinterpret_cast<uint2*>(out + r * ldo + c) = w;
+    if (planes == 2) {
+        w.x = pack_h2(lo_part(v.x, bf16), lo_part(v.y, bf16), bf16);
+        w.y = pack_h2(lo_part(v.z, bf16), lo_part(v.w, bf16), bf16);
+        *reinterpret_cast<uint2*>(out + plane + r * ldo + c) = w;
+    }
+}
+
+template <int NTERMS, int FMT>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams& p, cudaStream_t stream) {
+    using C_ = Cfg<NTERMS>;
+    auto kern = gemm_tc_kernel<NTERMS, FMT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
+        return VCR_ERR_LAUNCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)vcr_cdiv(p.M, BM) * vcr_cdiv(p.N, BN) * p.nb_outer * p.nb_inner;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    kern<<<grid, 256, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+}  // namespace
+
+vcr_tmap_encode_fn vcr_get_tmap_encoder() {
+    static vcr_tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<vcr_tmap_encode_fn>(ptr);
+    }
+    return fn;
+}
+
+int vcr_make_operand_tmap(CUtensorMap* out, const void* base, int cols, long long rows, int ld_elems,
+                          long long plane_stride_elems, int planes, int box_rows) {
+    vcr_tmap_encode_fn enc = vcr_get_tmap_encoder();
+    if (!enc) return VCR_ERR_LAUNCH;
+    if ((ld_elems & 7) || (reinterpret_cast<uintptr_t>(base) & 15) || (plane_stride_elems & 7)) return VCR_ERR_INVALID;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(planes > 0 ? planes : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)(planes > 1 ? plane_stride_elems : (long long)ld_elems * rows) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? VCR_OK : VCR_ERR_INVALID;
+}
+
+// Tensor-core GEMM on operand-format inputs.
+//   A: [a_planes][a_rows_total][lda] 16-bit, B likewise (both K-major).  mode: 0 = fp16 split 3-term ("h3"),
+//   1 = fp16 single, 2 = bf16 single.  Per batch z = (zo, zi): A rows start at zo*a_row_o + zi*a_row_i and its
+//   K range at column zo*a_col_o + zi*a_col_i (same for B); M, N, K are per batch.
+//   Outputs (each optional): C fp32 (+residual R), H operand-format row-major for columns < h_split,
+//   HT operand-format transposed for columns >= h_split.  out_planes 2 writes hi+lo, 1 hi only.
+VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_cols_total, long long a_plane,
+                        long long a_row_o, long long a_row_i, int a_col_o, int a_col_i,
+                        const void* B, int ldb, long long b_rows_total, int b_cols_total, long long b_plane,
+                        long long b_row_o, long long b_row_i, int b_col_o, int b_col_i,
+                        int M, int N, int K, int nb_outer, int nb_inner, int mode,
+                        float alpha, const float* bias, int act, float slope,
+                        float* C, int ldc, long long c_so, long long c_si,
+                        const float* R, int ldr, long long r_so, long long r_si,
+                        void* H, int ldh, long long h_plane, long long h_so, long long h_si, int h_split,
+                        void* HT, int ldt, long long t_plane, long long t_so, long long t_si,
+                        int out_planes, cudaStream_t stream) {
+    VCR_REQUIRE(A && B && M > 0 && N > 0 && K > 0 && nb_outer > 0 && nb_inner > 0);   // no output at all = timing probe
+    if (mode < 0 || mode > 2) return VCR_ERR_INVALID;
+    if (((a_col_o | a_col_i | b_col_o | b_col_i) != 0) && (K % BK) != 0) return VCR_ERR_UNSUPPORTED;
+    const int planes = mode == 0 ? 2 : 1;
+    CUtensorMap tmA, tmB;
+    int rc = vcr_make_operand_tmap(&tmA, A, a_cols_total, a_rows_total, lda, a_plane, planes, BM);
+    if (rc != VCR_OK) return rc;
+    rc = vcr_make_operand_tmap(&tmB, B, b_cols_total, b_rows_total, ldb, b_plane, planes, BN);
+    if (rc != VCR_OK) return rc;
+    TcGemmParams p;
+    p.M = M; p.N = N; p.K = K; p.nb_outer = nb_outer; p.nb_inner = nb_inner;
+    p.a_row_o = a_row_o; p.a_row_i = a_row_i; p.a_col_o = a_col_o; p.a_col_i = a_col_i;
+    p.b_row_o = b_row_o; p.b_row_i = b_row_i; p.b_col_o = b_col_o; p.b_col_i = b_col_i;
+    p.alpha = alpha; p.bias = bias; p.act = act; p.slope = slope;
+    p.C = C; p.ldc = ldc; p.c_so = c_so; p.c_si = c_si;
+    p.R = R; p.ldr = ldr; p.r_so = r_so; p.r_si = r_si;
+    p.H = reinterpret_cast<__half*>(H); p.ldh = ldh; p.h_plane = h_plane; p.h_so = h_so; p.h_si = h_si;
+    p.h_split = H ? (HT ? h_split : N) : 0;
+    p.HT = reinterpret_cast<__half*>(HT); p.ldt = ldt; p.t_plane = t_plane; p.t_so = t_so; p.t_si = t_si;
+    p.out_planes = out_planes; p.out_bf16 = mode == 2;
+    { const char* e = getenv("VCR_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    if (mode == 0) return launch_tc<3, 0>(tmA, tmB, p, stream);
+    if (mode == 1) return launch_tc<1, 0>(tmA, tmB, p, stream);
+    return launch_tc<1, 1>(tmA, tmB, p, stream);
+}
+
+// fp32 [rows, cols] (row stride ld) -> operand format [planes][rows][ldo] (fp16, or bf16 when bf16 != 0)
+VCR_API int vcr_to_operand(const float* x, int ld, long long rows, int cols, void* out, int ldo, long long plane_stride,
+                           int planes, int bf16, cudaStream_t stream) {
+    VCR_REQUIRE(x && out && rows > 0 && cols > 0 && (planes == 1 || planes == 2));
+    if ((cols & 3) || (ld & 3) || (ldo & 3)) return VCR_ERR_INVALID;
+    const long long n = rows * (cols >> 2);
+    to_operand_kernel<<<vcr_cdiv(n, 256), 256, 0, stream>>>(x, ld, rows, cols, reinterpret_cast<__half*>(out), ldo,
+                                                            plane_stride, planes, bf16);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}

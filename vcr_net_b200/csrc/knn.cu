@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int QPB = 32;       // queries per CTA (one per lane)
-constexpr int NWARP = 8;      // candidate slices
+constexpr int NWARP = 2;      // candidate slices (the final lexicographic merge is serial per query: keep it short)
 constexpr int TJ = 128;       // candidates per smem tile
 constexpr int CPW = TJ / NWARP;
 

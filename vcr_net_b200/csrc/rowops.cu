@@ -2,7 +2,7 @@
 // module boundary, the 3->64 pointwise conv, the reference's custom LayerNorm, row softmax (with the
 // partial-overlap key mask), column statistics of attention probabilities, and the soft
 // virtual-correspondence reduction.  One warp per row, float4 accesses, no shared memory.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -152,6 +152,127 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int slabs, i
     float s = 0.f;
     for (int t = 0; t < slabs; ++t) s += part[((size_t)b * slabs + t) * n + j];
     out[(size_t)b * n + j] = s;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Operand-format producers for the tensor-core GEMMs (gemm_tc.cu): LayerNorm and softmax write the
+// 16-bit hi/lo planes directly, so no separate conversion pass sits between them and the next GEMM.
+// ---------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void layernorm_operand_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
+                                         const float* __restrict__ b, float eps, int M, int D,
+                                         __half* __restrict__ out, int ldo, long long plane, int planes, int bf16) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i] = xr[lane + i * 32];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float den = sqrtf(warp_sum(q) / (float)(D - 1)) + eps;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    __half* o = out + (size_t)row * ldo;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 aa = a4[lane + i * 32], bb = b4[lane + i * 32];
+        float4 r;
+        r.x = aa.x * v[i].x / den + bb.x; r.y = aa.y * v[i].y / den + bb.y;
+        r.z = aa.z * v[i].z / den + bb.z; r.w = aa.w * v[i].w / den + bb.w;
+        const int c = (lane + i * 32) * 4;
+        *reinterpret_cast<uint2*>(o + c) = make_uint2(tc::pack_h2(r.x, r.y, bf16), tc::pack_h2(r.z, r.w, bf16));
+        if (planes == 2)
+            *reinterpret_cast<uint2*>(o + plane + c) =
+                make_uint2(tc::pack_h2(tc::lo_part(r.x, bf16), tc::lo_part(r.y, bf16), bf16),
+                           tc::pack_h2(tc::lo_part(r.z, bf16), tc::lo_part(r.w, bf16), bf16));
+    }
+}
+
+// row statistics of the (optionally key-masked) softmax: m_i = max_j s_ij, z_i = sum_j exp(s_ij - m_i)
+__global__ void row_lse_kernel(const float* __restrict__ S, int ld, long long rows, int n,
+                               const uint8_t* __restrict__ keep, long long rows_per_batch,
+                               float* __restrict__ rmax, float* __restrict__ rsum) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* r = S + row * ld;
+    const uint8_t* kp = keep ? keep + (row / rows_per_batch) * n : nullptr;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        s += expf(v - m);
+    }
+    s = warp_sum(s);
+    if (lane == 0) { rmax[row] = m; rsum[row] = s; }
+}
+
+// S fp32 -> softmax probabilities in operand format (S is left untouched)
+__global__ void softmax_operand_kernel(const float* __restrict__ S, int ld, long long rows, int n,
+                                       const uint8_t* __restrict__ keep, long long rows_per_batch,
+                                       __half* __restrict__ out, int ldo, long long plane, int planes, int bf16) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* r = S + row * ld;
+    const uint8_t* kp = keep ? keep + (row / rows_per_batch) * n : nullptr;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        s += expf(v - m);
+    }
+    s = warp_sum(s);
+    unsigned short* o = reinterpret_cast<unsigned short*>(out + row * ldo);
+    for (int j = lane; j < n; j += 32) {
+        float v = r[j];
+        if (kp && !kp[j]) v = -1e9f;
+        const float pj = expf(v - m) / s;
+        o[j] = (unsigned short)(tc::pack_h2(pj, 0.f, bf16) & 0xffff);
+        if (planes == 2) o[plane + j] = (unsigned short)(tc::pack_h2(tc::lo_part(pj, bf16), 0.f, bf16) & 0xffff);
+    }
+}
+
+// colsum[b, j] = sum over rows i of batch b of exp(S_ij - m_i) / z_i  (deterministic slab order)
+__global__ void colsum_softmax_partial_kernel(const float* __restrict__ S, int ld, long long rows_per_batch, int n,
+                                              const float* __restrict__ rmax, const float* __restrict__ rsum,
+                                              int slabs, float* __restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slab = blockIdx.y, b = blockIdx.z;
+    if (j >= n) return;
+    const long long per = (rows_per_batch + slabs - 1) / slabs;
+    const long long r0 = slab * per, r1 = min(rows_per_batch, r0 + per);
+    const long long base = (long long)b * rows_per_batch;
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r)
+        acc += expf(S[(base + r) * ld + j] - rmax[base + r]) / rsum[base + r];
+    part[((size_t)b * slabs + slab) * n + j] = acc;
 }
 
 // rowsum[r] = sum_j P[r, j]   (model/vcrnet_model.py:244 after the dim=1 softmax)
@@ -389,6 +510,59 @@ VCR_API int vcr_colsum(const float* P, int ld, int B, long long rows_per_batch, 
     float* part = reinterpret_cast<float*>(workspace);
     dim3 g(vcr_cdiv(n, 128), slabs, B);
     colsum_partial_kernel<<<g, 128, 0, stream>>>(P, ld, rows_per_batch, n, slabs, part);
+    VCR_CHECK_LAUNCH();
+    dim3 g2(vcr_cdiv(n, 128), B);
+    colsum_final_kernel<<<g2, 128, 0, stream>>>(part, slabs, n, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+
+VCR_API int vcr_layernorm_operand(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                                  void* out, int ldo, long long plane_stride, int planes, int bf16, cudaStream_t stream) {
+    VCR_REQUIRE(x && a && b && out && M > 0 && (planes == 1 || planes == 2));
+    if (D % 128 != 0 || D > 1024 || (ldx & 3) || (ldo & 3)) return VCR_ERR_UNSUPPORTED;
+    const int wpb = 8;
+    dim3 g(vcr_cdiv(M, wpb));
+    __half* o = reinterpret_cast<__half*>(out);
+    switch (D / 128) {
+#define LN_CASE(V) case V: layernorm_operand_kernel<V><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, o, ldo, plane_stride, planes, bf16); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+    }
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_row_lse(const float* S, int ld, long long rows, int n, const uint8_t* keep, long long rows_per_batch,
+                        float* rmax, float* rsum, cudaStream_t stream) {
+    VCR_REQUIRE(S && rmax && rsum && rows > 0 && n > 0 && (!keep || rows_per_batch > 0));
+    row_lse_kernel<<<vcr_cdiv(rows, 8), 256, 0, stream>>>(S, ld, rows, n, keep, rows_per_batch, rmax, rsum);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API int vcr_softmax_operand(const float* S, int ld, long long rows, int n, const uint8_t* keep,
+                                long long rows_per_batch, void* out, int ldo, long long plane_stride, int planes,
+                                int bf16, cudaStream_t stream) {
+    VCR_REQUIRE(S && out && rows > 0 && n > 0 && (!keep || rows_per_batch > 0) && (planes == 1 || planes == 2));
+    softmax_operand_kernel<<<vcr_cdiv(rows, 8), 256, 0, stream>>>(S, ld, rows, n, keep, rows_per_batch,
+                                                                 reinterpret_cast<__half*>(out), ldo, plane_stride,
+                                                                 planes, bf16);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// column sums of softmax(S) per batch without materialising the probabilities (workspace as vcr_colsum)
+VCR_API int vcr_colsum_softmax(const float* S, int ld, int B, long long rows_per_batch, int n, const float* rmax,
+                               const float* rsum, float* out, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
+    VCR_REQUIRE(S && rmax && rsum && out && B > 0 && rows_per_batch > 0 && n > 0 && B <= 65535);
+    const int slabs = 32;
+    if (!workspace || workspace_bytes < vcr_colsum_workspace_bytes(B, n)) return VCR_ERR_WORKSPACE;
+    float* part = reinterpret_cast<float*>(workspace);
+    dim3 g(vcr_cdiv(n, 128), slabs, B);
+    colsum_softmax_partial_kernel<<<g, 128, 0, stream>>>(S, ld, rows_per_batch, n, rmax, rsum, slabs, part);
     VCR_CHECK_LAUNCH();
     dim3 g2(vcr_cdiv(n, 128), B);
     colsum_final_kernel<<<g2, 128, 0, stream>>>(part, slabs, n, out);

@@ -14,7 +14,7 @@ import math
 
 import torch
 
-from . import ops
+from . import config, ops
 
 _F32 = torch.float32
 
@@ -94,7 +94,14 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
         idx_xyz = ops.knn_topk(xyz, k, token_major=False)                    # :129 (3-d kNN)
     pq3 = ops.gemm(cat[:, :, 128:256], W["sn1_w"], W["sn1_b"])               # [B,N,512] = [P3|Q3]
     ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_xyz, slope, cat[:, :, 256:512])  # :130-132
-    emb = ops.gemm(cat, W["w3"], W["b3"], act=1, slope=slope)                # :134-135
+    mode = config.precision
+    if mode == "fp32":
+        emb = ops.gemm(cat, W["w3"], W["b3"], act=1, slope=slope)            # :134-135
+    else:
+        w3 = packed(m, "w3_" + mode, [m.conv3_lpd.weight], lambda: ops.to_operand(W["w3"], mode))
+        emb = torch.empty((B, N, W["w3"].shape[0]), dtype=_F32, device=xyz.device)
+        ops.gemm_tc(ops.to_operand(cat, mode), w3, B * N, W["w3"].shape[0], 512, bias=W["b3"], act=1,
+                    slope=slope, c=emb)
     if stages is not None:
         stages.update(f64=h2, idx_feat=idx_feat, idx_xyz=idx_xyz, cat=cat)
     return emb
@@ -171,6 +178,8 @@ def encoder_decoder_tok(model, src: torch.Tensor, tgt: torch.Tensor, final_resid
     x + sublayer(norm(x)) (:147-153); the residual add rides in the epilogue of the last GEMM of
     each sublayer.  ``final_residual`` is added to the decoder's final LayerNorm output (the
     `emb + emb_p` of model/vcrnet_model.py:504-505)."""
+    if config.precision != "fp32":
+        return encoder_decoder_tc(model, src.contiguous(), tgt.contiguous(), final_residual, config.precision)
     x = src
     for layer in model.encoder.layers:
         n = _ln(layer.sublayer[0].norm, x)
@@ -186,6 +195,94 @@ def encoder_decoder_tok(model, src: torch.Tensor, tgt: torch.Tensor, final_resid
         y = mha_tok(layer.src_attn, n, mem, residual=y)
         n = _ln(layer.sublayer[2].norm, y)
         y = ffn_tok(layer.feed_forward, n, residual=y)
+    return _ln(model.decoder.norm, y, residual=final_residual)
+
+
+# --------------------------------------------------------------------------------------------------
+# Transformer on tensor cores (operand-format chaining, see csrc/gemm_tc.cu)
+# --------------------------------------------------------------------------------------------------
+
+def mha_weights_tc(m, mode):
+    W = mha_weights(m)
+    params = [p for l in m.linears for p in (l.weight, l.bias)]
+    return packed(m, "mha_" + mode, params, lambda: {
+        "wqkv": ops.to_operand(W["wqkv"], mode), "wq": ops.to_operand(W["wq"], mode),
+        "wkv": ops.to_operand(W["wkv"], mode), "wo": ops.to_operand(W["wo"], mode)})
+
+
+def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
+    """MultiHeadedAttention.forward (model/transformer.py:202-224) on tensor cores.
+
+    xq_op / xkv_op: operand-format LayerNorm outputs [B*N, D] (xkv_op None => self-attention).
+    Projections write Q, K row-major and V TRANSPOSED per head in operand format straight from the
+    GEMM epilogue; scores are one batched GEMM over (batch, head) addressed by row/column offsets."""
+    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+    D, h, dk = m.h * m.d_k, m.h, m.d_k
+    dev = residual.device
+    scale = 1.0 / math.sqrt(dk)
+    vt = ops.Operand.empty(B * D, Nk, mode, dev)                         # rows (b, head*dk + d), cols = keys
+    if xkv_op is None:
+        qk = ops.Operand.empty(B * Nq, 2 * D, mode, dev)
+        ops.gemm_tc(xq_op, Wt["wqkv"], Nq, 3 * D, D, nbo=B, a_off=(Nq, 0, 0, 0), bias=W["bqkv"],
+                    h=qk, h_strides=(Nq * qk.ld, 0), h_split=2 * D, ht=vt, ht_strides=(D * vt.ld, 0))
+        q_v, k_v = qk.cols_view(0, D), qk.cols_view(D, D)
+    else:
+        q_v = ops.Operand.empty(B * Nq, D, mode, dev)
+        ops.gemm_tc(xq_op, Wt["wq"], B * Nq, D, D, bias=W["bq"], h=q_v, h_split=D)
+        k_v = ops.Operand.empty(B * Nk, D, mode, dev)
+        ops.gemm_tc(xkv_op, Wt["wkv"], Nk, 2 * D, D, nbo=B, a_off=(Nk, 0, 0, 0), bias=W["bkv"],
+                    h=k_v, h_strides=(Nk * k_v.ld, 0), h_split=D, ht=vt, ht_strides=(D * vt.ld, 0))
+    att = ops.Operand.empty(B * Nq, D, mode, dev)
+    ldS = (Nk + 3) // 4 * 4
+    per_b = h * Nq * ldS * 4 * 2
+    cb = max(1, min(B, max_ws_bytes // per_b))
+    S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
+    for b0 in range(0, B, cb):
+        nb = min(cb, B - b0)
+        ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
+                    a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S, c_strides=(h * Nq * ldS, Nq * ldS))
+        Sv = S[:nb].view(nb * h * Nq, ldS)
+        keep = None
+        if m.is_src:                                                     # partial overlap (:35-53)
+            csum = ops.colsum_softmax(Sv, Nk, nb)
+            _, keep = ops.topk_select(csum, int(Nk * m.overlap2), want_idx=False, want_mask=True)
+        P = ops.softmax_operand(Sv, Nk, mode, keep=keep, rows_per_batch=h * Nq)
+        ops.gemm_tc(P, vt.rows_view(b0 * D, nb * D), Nq, dk, Nk, nbo=nb, nbi=h, a_off=(h * Nq, Nq, 0, 0),
+                    b_off=(D, dk, 0, 0), h=att.rows_view(b0 * Nq, nb * Nq), h_strides=(Nq * att.ld, dk), h_split=dk)
+    out = torch.empty((B, Nq, D), dtype=_F32, device=dev)
+    ops.gemm_tc(att, Wt["wo"], B * Nq, D, D, bias=W["bo"], c=out, residual=residual)
+    return out
+
+
+def ffn_tc(m, n_op, rows, residual, mode):
+    """PositionwiseFeedForward (model/transformer.py:237-238); the hidden activation never exists in fp32."""
+    w = packed(m, "ffn_" + mode, [m.w_1.weight, m.w_2.weight],
+               lambda: (ops.to_operand(m.w_1.weight.detach(), mode), ops.to_operand(m.w_2.weight.detach(), mode)))
+    F_, D = m.w_1.weight.shape
+    hid = ops.Operand.empty(rows, F_, mode, residual.device)
+    ops.gemm_tc(n_op, w[0], rows, F_, D, bias=m.w_1.bias, act=1, slope=0.0, h=hid, h_split=F_)
+    out = torch.empty_like(residual)
+    ops.gemm_tc(hid, w[1], rows, D, F_, bias=m.w_2.bias, c=out, residual=residual)
+    return out
+
+
+def _ln_op(norm, x, mode):
+    return ops.layernorm_operand(x, norm.a_2, norm.b_2, norm.eps, mode)
+
+
+def encoder_decoder_tc(model, src, tgt, final_residual, mode):
+    B, Ns, D = src.shape
+    Nt = tgt.shape[1]
+    x = src
+    for layer in model.encoder.layers:
+        x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, Ns, Ns, x, mode)
+        x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * Ns, x, mode)
+    mem = _ln_op(model.encoder.norm, x, mode)
+    y = tgt
+    for layer in model.decoder.layers:
+        y = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, y, mode), None, B, Nt, Nt, y, mode)
+        y = mha_tc(layer.src_attn, _ln_op(layer.sublayer[1].norm, y, mode), mem, B, Nt, Ns, y, mode)
+        y = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[2].norm, y, mode), B * Nt, y, mode)
     return _ln(model.decoder.norm, y, residual=final_residual)
 
 
@@ -209,11 +306,26 @@ def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_inp
 # VCP head
 # --------------------------------------------------------------------------------------------------
 
+def pair_dots(src_tok, tgt_tok):
+    """dot[b,i,j] = s_i . t_j (the matmul of model/vcrnet_model.py:337): fp32 SIMT or 3-term tensor cores.
+    The throughput modes keep the 3-term split here: these logits cancel catastrophically
+    (|f|^2 ~ 500 against gaps < 1), SURVEY.md section 7 hard part 2."""
+    if config.precision == "fp32":
+        return ops.pair_dots(src_tok, tgt_tok)
+    B, Ns, D = src_tok.shape
+    Nt = tgt_tok.shape[1]
+    ld = (Nt + 3) // 4 * 4
+    dot = torch.empty((B, Ns, ld), dtype=_F32, device=src_tok.device)
+    ops.gemm_tc(ops.to_operand(src_tok, "h3"), ops.to_operand(tgt_tok, "h3"), Ns, Nt, D, nbo=B,
+                a_off=(Ns, 0, 0, 0), b_off=(Nt, 0, 0, 0), c=dot, c_strides=(Ns * ld, 0))
+    return dot, ld
+
+
 def vcp_whole(src_tok, tgt_tok, tgt_xyz):
     """getCopairALL (model/vcrnet_model.py:334-347): src_corr [B,3,N]."""
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
-    dot, ld = ops.pair_dots(src_tok, tgt_tok)
+    dot, ld = pair_dots(src_tok, tgt_tok)
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
     corr, _, _ = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=tgt_xyz.contiguous(), mode=0)
     return corr
@@ -226,7 +338,7 @@ def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):
     srcK = int(Ns * 0.84 * overlap2)
     tgtK = int(Nt * 0.84 * overlap2)
     src_tok, tgt_tok = src_tok.contiguous(), tgt_tok.contiguous()
-    dot, ld = ops.pair_dots(src_tok, tgt_tok)
+    dot, ld = pair_dots(src_tok, tgt_tok)
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
     pd = ops.negdist_(dot, ld, Ns, Nt, xx, yy)                        # scores (:213-214)
     row_stat = ops.rowsum_colsoftmax(pd, ld, Ns, Nt)                  # softmax over dim=1, sum dim=2 (:243-244)
@@ -244,7 +356,7 @@ def vcp_copair(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
     srcK = int(Ns * 0.52 * overlap2)
-    dot, ld = ops.pair_dots(src_tok, tgt_tok)
+    dot, ld = pair_dots(src_tok, tgt_tok)
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
     _, best_i, best_v = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
     keep, _ = ops.topk_select(best_v, srcK)                            # [B,srcK] sorted by confidence

@@ -132,6 +132,119 @@ def bgemm(a, a_ld, a_so, a_si, b, b_ld, b_so, b_si, b_layout, c, c_ld, c_so, c_s
 
 
 # --------------------------------------------------------------------------------------------------
+# tensor-core GEMM on operand-format buffers
+# --------------------------------------------------------------------------------------------------
+
+TC_MODES = {"h3": 0, "fp16": 1, "bf16": 2}
+
+
+class Operand:
+    """16-bit K-major operand buffer [planes, rows, ld] for vcr_gemm_tc: plane 0 = hi = fp16(x),
+    plane 1 = lo = fp16((x - hi) * 2^11) in the 3-term "h3" mode; one plane in fp16 / bf16 modes.
+    Views (column / row sub-ranges) share the storage and only move the base pointer."""
+
+    def __init__(self, buf, rows, cols, ld, planes, plane_stride, ptr, mode):
+        self.buf, self.rows, self.cols, self.ld = buf, rows, cols, ld
+        self.planes, self.plane_stride, self.ptr, self.mode = planes, plane_stride, ptr, mode
+
+    @staticmethod
+    def empty(rows, cols, mode="h3", device="cuda"):
+        planes = 2 if mode == "h3" else 1
+        dt = torch.bfloat16 if mode == "bf16" else torch.float16
+        ld = (cols + 7) // 8 * 8
+        buf = torch.empty((planes, rows, ld), dtype=dt, device=device)
+        return Operand(buf, rows, cols, ld, planes, rows * ld, buf.data_ptr(), mode)
+
+    def cols_view(self, c0, ncols):
+        assert c0 % 8 == 0
+        return Operand(self.buf, self.rows, ncols, self.ld, self.planes, self.plane_stride, self.ptr + 2 * c0, self.mode)
+
+    def rows_view(self, r0, nrows):
+        return Operand(self.buf, nrows, self.cols, self.ld, self.planes, self.plane_stride,
+                       self.ptr + 2 * r0 * self.ld, self.mode)
+
+    def to_float(self):
+        x = self.buf[0, :, :self.cols].float()
+        if self.planes == 2:
+            x = x + self.buf[1, :, :self.cols].float() / 2048.0
+        return x
+
+
+def to_operand(x: torch.Tensor, mode="h3") -> Operand:
+    """fp32 rows [.., cols] -> operand format."""
+    _chk(x, "x")
+    rows, cols, ld = _rows(x)
+    out = Operand.empty(rows, cols, mode, x.device)
+    L = lib()
+    L.check(L.vcr_to_operand(x.data_ptr(), ld, rows, cols, out.ptr, out.ld, out.plane_stride,
+                             out.planes, int(mode == "bf16"), _stream(x)), "vcr_to_operand")
+    return out
+
+
+def gemm_tc(a: Operand, b: Operand, M, N, K, *, nbo=1, nbi=1,
+            a_off=(0, 0, 0, 0), b_off=(0, 0, 0, 0), alpha=1.0, bias=None, act=0, slope=0.0,
+            c=None, c_strides=(0, 0), residual=None, r_strides=(0, 0),
+            h: Operand | None = None, h_strides=(0, 0), h_split=0,
+            ht: Operand | None = None, ht_strides=(0, 0)):
+    """C[z] = act(alpha*A[z] B[z]^T + bias) + residual on tensor cores; see include/vcr_b200.h."""
+    L = lib()
+    ldc = c.stride(-2) if c is not None else 0
+    ldr = residual.stride(-2) if residual is not None else 0
+    outp = h if h is not None else ht
+    L.check(L.vcr_gemm_tc(
+        a.ptr, a.ld, a.rows, a.cols, a.plane_stride, *a_off,
+        b.ptr, b.ld, b.rows, b.cols, b.plane_stride, *b_off,
+        M, N, K, nbo, nbi, TC_MODES[a.mode], float(alpha), bias.data_ptr() if bias is not None else None,
+        int(act), float(slope),
+        c.data_ptr() if c is not None else None, ldc, *c_strides,
+        residual.data_ptr() if residual is not None else None, ldr, *r_strides,
+        h.ptr if h is not None else None, h.ld if h is not None else 0,
+        h.plane_stride if h is not None else 0, *h_strides, h_split,
+        ht.ptr if ht is not None else None, ht.ld if ht is not None else 0,
+        ht.plane_stride if ht is not None else 0, *ht_strides,
+        outp.planes if outp is not None else 1, _stream(a.buf)), "vcr_gemm_tc")
+
+
+def layernorm_operand(x: torch.Tensor, a, b, eps, mode) -> Operand:
+    _chk(x, "x")
+    M, D, ldx = _rows(x)
+    out = Operand.empty(M, D, mode, x.device)
+    L = lib()
+    L.check(L.vcr_layernorm_operand(x.data_ptr(), ldx, a.data_ptr(), b.data_ptr(), float(eps), M, D, out.ptr,
+                                    out.ld, out.plane_stride, out.planes, int(mode == "bf16"), _stream(x)),
+            "vcr_layernorm_operand")
+    return out
+
+
+def softmax_operand(S: torch.Tensor, n: int, mode, keep=None, rows_per_batch=0) -> Operand:
+    """S fp32 [rows, ld] (first n columns valid) -> probabilities in operand format [rows, n]."""
+    rows, _, ld = _rows(S)
+    out = Operand.empty(rows, n, mode, S.device)
+    L = lib()
+    L.check(L.vcr_softmax_operand(S.data_ptr(), ld, rows, n, keep.data_ptr() if keep is not None else None,
+                                  rows_per_batch, out.ptr, out.ld, out.plane_stride, out.planes,
+                                  int(mode == "bf16"), _stream(S)), "vcr_softmax_operand")
+    return out
+
+
+def colsum_softmax(S: torch.Tensor, n: int, B: int):
+    """column sums per batch of softmax(S) over rows, S fp32 [B*rows_per_batch, ld] left untouched."""
+    rows, _, ld = _rows(S)
+    dev = S.device
+    rmax = torch.empty(rows, dtype=_F32, device=dev)
+    rsum = torch.empty(rows, dtype=_F32, device=dev)
+    out = torch.empty((B, n), dtype=_F32, device=dev)
+    L = lib()
+    st = _stream(S)
+    L.check(L.vcr_row_lse(S.data_ptr(), ld, rows, n, None, 0, rmax.data_ptr(), rsum.data_ptr(), st), "vcr_row_lse")
+    wsb = L.vcr_colsum_workspace_bytes(B, n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.check(L.vcr_colsum_softmax(S.data_ptr(), ld, B, rows // B, n, rmax.data_ptr(), rsum.data_ptr(), out.data_ptr(),
+                                 ws.data_ptr(), wsb, st), "vcr_colsum_softmax")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # LPDNet pieces
 # --------------------------------------------------------------------------------------------------
 
