@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
     using C_ = Cfg<NTERMS>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::NSTAGES * C_::STAGE_BYTES);
     uint64_t* full = bars;                         // [NSTAGES]
     uint64_t* empty = bars + C_::NSTAGES;          // [NSTAGES]
@@ -159,8 +159,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> registers -> global =====================
+        // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
+        // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per load).  Row-major
+        // outputs are transposed through a swizzled per-warp smem tile so that each global access of the
+        // warp covers whole 128-byte row segments; alpha / bias / activation / residual are applied in that
+        // coalesced layout, where a lane owns the same 4 columns for all rows (bias lives in 4 registers).
+        // The transposed operand output (V^T) is stored straight from the row-per-thread layout, where
+        // consecutive lanes are consecutive rows, i.e. already coalesced.
         const int ew = warp - 4;                               // == warp % 4: TMEM lane quarter
+        const float alpha = p.alpha, slope = p.slope;
+        const int act = p.act, obf = p.out_bf16, nplanes = p.out_planes;
+        const int N = p.N, M = p.M, h_split = p.h_split;
+        const int ldc = p.ldc, ldr = p.ldr, ldh = p.ldh;
+        const bool vecC = (ldc & 3) == 0, vecR = (ldr & 3) == 0, vecH = (ldh & 3) == 0;
+        float* stg = stage_buf + ew * (32 * 32);
+        const int c4 = lane & 7, rsub = lane >> 3;
         int it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
@@ -171,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc::mbar_wait(&tfull[a], aph);
             tc::tc_fence_after();
             const int row = m_blk * BM + ew * 32 + lane;
-            const bool row_ok = row < p.M;
+            const bool row_ok = row < M;
             const uint32_t tadr = tmem_base + a * C_::ACC_COLS + ((uint32_t)(ew * 32) << 16);
             float* Cz = p.C ? p.C + zo * p.c_so + zi * p.c_si : nullptr;
             const float* Rz = p.R ? p.R + zo * p.r_so + zi * p.r_si : nullptr;
@@ -180,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int col0 = n_blk * BN + c0;
-                if (col0 >= p.N) break;                        // warp-uniform
+                if (col0 >= N) break;                          // warp-uniform
                 uint32_t r0[32];
                 float v[32];
                 tc::tmem_ld_32x32(tadr + c0, r0);
@@ -195,88 +208,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
                 }
-                const bool full_chunk = col0 + 32 <= p.N;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t2 = p.alpha * v[j];
-                    if (p.bias && col0 + j < p.N) t2 += p.bias[col0 + j];
-                    if (p.act == 1) t2 = leaky(t2, p.slope);
-                    v[j] = t2;
-                }
-                if (Tz && row_ok && col0 + 32 > p.h_split) {
-                    // operand-format transposed: HT[plane][col - h_split][row]; lanes = consecutive rows,
-                    // so this direct store from the one-row-per-thread TMEM layout is already coalesced
-                    for (int pl = 0; pl < p.out_planes; ++pl) {
-                        unsigned short* tt = reinterpret_cast<unsigned short*>(Tz + pl * p.t_plane);
+                if (Tz && col0 + 32 > h_split) {               // warp-uniform: transposed operand output
+                    if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = col0 + j;
-                            if (col < p.N && col >= p.h_split) {
-                                const float x = pl == 0 ? v[j] : lo_part(v[j], p.out_bf16);
-                                const uint32_t w = pack_h2(x, 0.f, p.out_bf16);
-                                tt[(size_t)(col - p.h_split) * p.ldt + row] = (unsigned short)(w & 0xffff);
+                            if (col < N && col >= h_split) {
+                                float x = alpha * v[j];
+                                if (p.bias) x += __ldg(p.bias + col);
+                                if (act == 1) x = leaky(x, slope);
+                                unsigned short* tt = reinterpret_cast<unsigned short*>(Tz) + (size_t)(col - h_split) * p.ldt + row;
+                                tt[0] = (unsigned short)(pack_h2(x, 0.f, obf) & 0xffff);
+                                if (nplanes == 2) tt[p.t_plane] = (unsigned short)(pack_h2(lo_part(x, obf), 0.f, obf) & 0xffff);
                             }
                         }
                     }
                 }
-                const bool want_rm = (Cz != nullptr) || (Hz && col0 < p.h_split);
-                if (!want_rm || p.debug == 2) continue;                         // warp-uniform
-                // ---- row-major outputs: transpose through a swizzled smem tile so that every global
-                //      access of the warp covers whole 128-byte rows (4 rows x 128 B per instruction) ----
-                float* stg = stage_buf + ew * (32 * 32);
+                const bool want_h = Hz && col0 < h_split;
+                if ((Cz == nullptr && !want_h) || p.debug == 2) continue;        // warp-uniform
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
                         make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                const int c4 = lane & 7, rsub = lane >> 3;
+                const int col = col0 + c4 * 4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) {
+                    if (col + 4 <= N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    else {
+                        if (col < N) b4.x = p.bias[col];
+                        if (col + 1 < N) b4.y = p.bias[col + 1];
+                        if (col + 2 < N) b4.z = p.bias[col + 2];
+                    }
+                }
+                const bool vec = col + 4 <= N;
+                if (col < N) {
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int rl = itr * 4 + rsub;
-                    const int grow = m_blk * BM + ew * 32 + rl;
-                    float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
-                    const int col = col0 + c4 * 4;
-                    if (grow >= p.M || col >= p.N) continue;
-                    const bool vec = col + 4 <= p.N;
-                    if (Rz) {
-                        const float* rr = Rz + (size_t)grow * p.ldr + col;
-                        if (vec && (p.ldr & 3) == 0) {
-                            const float4 q = *reinterpret_cast<const float4*>(rr);
-                            x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                        } else {
-                            x.x += rr[0];
-                            if (col + 1 < p.N) x.y += rr[1];
-                            if (col + 2 < p.N) x.z += rr[2];
-                            if (col + 3 < p.N) x.w += rr[3];
-                        }
-                    }
-                    if (p.debug == 1) { if (x.x == 123.456f) Cz[0] = x.y; continue; }
-                    if (Cz) {
-                        float* cc = Cz + (size_t)grow * p.ldc + col;
-                        if (vec && (p.ldc & 3) == 0) {
-                            *reinterpret_cast<float4*>(cc) = x;
-                        } else {
-                            cc[0] = x.x;
-                            if (col + 1 < p.N) cc[1] = x.y;
-                            if (col + 2 < p.N) cc[2] = x.z;
-                            if (col + 3 < p.N) cc[3] = x.w;
-                        }
-                    }
-                    if (Hz && col < p.h_split) {
-                        for (int pl = 0; pl < p.out_planes; ++pl) {
-                            __half* hh = Hz + pl * p.h_plane + (size_t)grow * p.ldh + col;
-                            const float y0 = pl == 0 ? x.x : lo_part(x.x, p.out_bf16);
-                            const float y1 = pl == 0 ? x.y : lo_part(x.y, p.out_bf16);
-                            const float y2 = pl == 0 ? x.z : lo_part(x.z, p.out_bf16);
-                            const float y3 = pl == 0 ? x.w : lo_part(x.w, p.out_bf16);
-                            if (vec && col + 4 <= p.h_split && (p.ldh & 3) == 0) {
-                                *reinterpret_cast<uint2*>(hh) = make_uint2(pack_h2(y0, y1, p.out_bf16), pack_h2(y2, y3, p.out_bf16));
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int rl = itr * 4 + rsub;
+                        const int grow = m_blk * BM + ew * 32 + rl;
+                        if (grow >= M) continue;
+                        float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+                        x.x = fmaf(alpha, x.x, b4.x); x.y = fmaf(alpha, x.y, b4.y);
+                        x.z = fmaf(alpha, x.z, b4.z); x.w = fmaf(alpha, x.w, b4.w);
+                        if (act == 1) { x.x = leaky(x.x, slope); x.y = leaky(x.y, slope); x.z = leaky(x.z, slope); x.w = leaky(x.w, slope); }
+                        if (p.debug == 1) { if (x.x == 123.456f) Cz[0] = x.y; continue; }
+                        if (Rz) {
+                            const float* rr = Rz + (size_t)grow * ldr + col;
+                            if (vec && vecR) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(rr));
+                                x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
                             } else {
-                                const float ys[4] = {y0, y1, y2, y3};
-                                for (int q = 0; q < 4; ++q)
-                                    if (col + q < p.N && col + q < p.h_split)
-                                        reinterpret_cast<unsigned short*>(hh)[q] =
-                                            (unsigned short)(pack_h2(ys[q], 0.f, p.out_bf16) & 0xffff);
+                                x.x += rr[0];
+                                if (col + 1 < N) x.y += rr[1];
+                                if (col + 2 < N) x.z += rr[2];
+                                if (col + 3 < N) x.w += rr[3];
+                            }
+                        }
+                        if (Cz) {
+                            float* cc = Cz + (size_t)grow * ldc + col;
+                            if (vec && vecC) {
+                                *reinterpret_cast<float4*>(cc) = x;
+                            } else {
+                                cc[0] = x.x;
+                                if (col + 1 < N) cc[1] = x.y;
+                                if (col + 2 < N) cc[2] = x.z;
+                                if (col + 3 < N) cc[3] = x.w;
+                            }
+                        }
+                        if (want_h && col < h_split) {
+                            __half* hh = Hz + (size_t)grow * ldh + col;
+                            if (vec && col + 4 <= h_split && vecH) {
+                                *reinterpret_cast<uint2*>(hh) = make_uint2(pack_h2(x.x, x.y, obf), pack_h2(x.z, x.w, obf));
+                                if (nplanes == 2)
+                                    *reinterpret_cast<uint2*>(hh + p.h_plane) =
+                                        make_uint2(pack_h2(lo_part(x.x, obf), lo_part(x.y, obf), obf),
+                                                   pack_h2(lo_part(x.z, obf), lo_part(x.w, obf), obf));
+                            } else {
+                                const float ys[4] = {x.x, x.y, x.z, x.w};
+                                for (int q = 0; q < 4; ++q) {
+                                    if (col + q < N && col + q < h_split) {
+                                        reinterpret_cast<unsigned short*>(hh)[q] = (unsigned short)(pack_h2(ys[q], 0.f, obf) & 0xffff);
+                                        if (nplanes == 2)
+                                            reinterpret_cast<unsigned short*>(hh + p.h_plane)[q] =
+                                                (unsigned short)(pack_h2(lo_part(ys[q], obf), 0.f, obf) & 0xffff);
+                                    }
+                                }
                             }
                         }
                     }
