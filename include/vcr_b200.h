@@ -86,6 +86,14 @@ int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_cols_total
                 void* H, int ldh, long long h_plane, long long h_so, long long h_si, int h_split,
                 void* HT, int ldt, long long t_plane, long long t_so, long long t_si,
                 int out_planes, cudaStream_t stream);
+/* Flash-style multi-head attention (model/transformer.py:13-55) on tcgen05/TMEM: softmax(Q K^T scale) V, d_k = 128,
+ * scores and probabilities never leave the SM.  Q [planes][B*Nq][ldq] (head hh = columns hh*128..), K likewise
+ * with B*Nk rows, VT [planes][B*H*128][ldv] (row (b*H+hh)*128+d, Nk key columns), O like Q.  keep: optional
+ * uint8 [B,Nk] key mask (masked keys get -1e9, :51-52); lse: optional [B,H,Nq] log2-domain log-sum-exp. */
+int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const void* K, int ldk, long long k_plane,
+                      const void* VT, int ldv, long long v_plane, int B, int H, int Nq, int Nk, int dk,
+                      int mode, float scale, const uint8_t* keep, void* O, int ldo, long long o_plane,
+                      float* lse, cudaStream_t stream);
 int vcr_to_operand(const float* x, int ld, long long rows, int cols, void* out, int ldo, long long plane_stride,
                    int planes, int bf16, cudaStream_t stream);
 

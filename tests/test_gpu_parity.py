@@ -430,3 +430,52 @@ def test_throughput_modes_reported_tolerance(net_whole, mode, tol):
     finally:
         config.set_precision(old)
     assert rel_err(nump(sp), g["src_p"]) < tol and rel_err(nump(tp), g["tgt_p"]) < tol
+
+
+# ---------------------------------------------------------------- flash attention (tcgen05) -------------
+def _attn_operands(q, k, v, mode):
+    """[B,h,N,dk] numpy -> (Q, K row-major operands [B*N, h*dk], V^T operand [B*h*dk, Nk])."""
+    B, h, Nq, dk = q.shape
+    Nk = k.shape[2]
+    tok = lambda x: cu(x.transpose(0, 2, 1, 3).reshape(x.shape[0] * x.shape[2], h * dk))
+    vt = cu(v.transpose(0, 1, 3, 2).reshape(B * h * dk, Nk))
+    return ops.to_operand(tok(q), mode), ops.to_operand(tok(k), mode), ops.to_operand(vt, mode)
+
+
+@pytest.mark.parametrize("mode,tol", [("h3", 2e-5), ("fp16", 3e-3), ("bf16", 3e-2)])
+def test_flash_attention_vs_golden(mode, tol):
+    g = load_golden("attention")
+    q, k, v = g["q"], g["k"], g["v"]
+    B, h, Nq, dk = q.shape
+    Nk = k.shape[2]
+    Q, K, VT = _attn_operands(q, k, v, mode)
+    out = ops.Operand.empty(B * Nq, h * dk, mode, DEV)
+    ops.flash_attn_tc(Q, K, VT, out, B, h, Nq, Nk, dk, 1.0 / np.sqrt(dk))
+    want = g["out"].transpose(0, 2, 1, 3).reshape(B * Nq, h * dk)
+    assert rel_err(nump(out.to_float()), want) < tol
+    keep = cu(g["kept"].astype(np.uint8))
+    ops.flash_attn_tc(Q, K, VT, out, B, h, Nq, Nk, dk, 1.0 / np.sqrt(dk), keep=keep)
+    want = g["out_src"].transpose(0, 2, 1, 3).reshape(B * Nq, h * dk)
+    assert rel_err(nump(out.to_float()), want) < tol
+
+
+@pytest.mark.parametrize("Nq,Nk,spread", [(1024, 1024, 1.0), (768, 768, 1.0), (300, 1000, 1.0), (256, 2048, 12.0)])
+def test_flash_attention_shapes_and_rescale(Nq, Nk, spread):
+    """Ragged tiles, many persistent work items per CTA and (spread = 12) logits whose running maximum
+    keeps growing, which exercises the lazy O-rescale path; oracle = numpy attention."""
+    rs = np.random.RandomState(Nq + Nk)
+    B, h, dk = 3, 4, 128
+    q = (rs.randn(B, h, Nq, dk) * spread).astype(np.float32)
+    k = rs.randn(B, h, Nk, dk).astype(np.float32)
+    k *= np.linspace(0.2, 1.5, Nk, dtype=np.float32)[None, None, :, None]      # later keys score higher
+    v = rs.randn(B, h, Nk, dk).astype(np.float32)
+    want, _ = O.attention(q, k, v)
+    Q, K, VT = _attn_operands(q, k, v, "h3")
+    out = ops.Operand.empty(B * Nq, h * dk, "h3", DEV)
+    lse = torch.empty(B, h, Nq, device=DEV)
+    ops.flash_attn_tc(Q, K, VT, out, B, h, Nq, Nk, dk, 1.0 / np.sqrt(dk), lse=lse)
+    got = nump(out.to_float()).reshape(B, Nq, h, dk).transpose(0, 2, 1, 3)
+    assert rel_err(got, want) < 3e-5
+    sc = (q.astype(np.float64) @ k.astype(np.float64).transpose(0, 1, 3, 2)) / np.sqrt(dk)
+    ref_lse = (np.log(np.exp(sc - sc.max(-1, keepdims=True)).sum(-1)) + sc.max(-1)) / np.log(2.0)
+    assert np.abs(nump(lse) - ref_lse).max() < 1e-3 * max(1.0, np.abs(ref_lse).max())

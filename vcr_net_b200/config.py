@@ -10,6 +10,8 @@ import os
 
 precision = os.environ.get("VCR_PRECISION", "h3")
 VALID = ("fp32", "h3", "fp16", "bf16")
+# flash attention kernel (attn_tc.cu) vs materialised scores through the GEMM kernel (tensor-core modes only)
+flash_attention = os.environ.get("VCR_FLASH", "1") != "0"
 
 
 def set_precision(p: str):

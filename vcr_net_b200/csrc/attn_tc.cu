@@ -1,0 +1,410 @@
+// Flash-style multi-head attention on tcgen05 / TMEM / TMA (sm_100a): softmax(Q K^T * scale) V for
+// d_k = 128 without ever writing the [B,h,Nq,Nk] score or probability tensors (reference
+// model/transformer.py:13-55 materialises both in fp32: 2 x 268 MB per call at B=16, N=1024).
+//
+// Work item = (batch, head, 128-query tile); persistent CTAs walk the items.  Per 64-key tile:
+//   warp 1 (one elected thread)  S = Q K_j^T          tcgen05.mma 128x64x16, S in TMEM (double-buffered)
+//   warps 4-7 (thread = query row) online softmax:    tcgen05.ld S -> exp2 -> P (fp16 hi/lo) -> smem
+//   warp 1                        O += P V_j           tcgen05.mma 128x128x16, O stays in TMEM
+//   warp 0 (one elected thread)  TMA: Q once per item, {K_j, V^T_j} through a 2-stage ring
+// QK^T of tile j+1 is issued before P V of tile j, so the tensor core works while the softmax warps
+// are busy.  O is rescaled LAZILY: the running maximum used for exp2 only moves when a row's new maximum
+// exceeds it by more than 2^8 (exact after the final 1/l normalisation, no overflow in fp16 P), so the
+// TMEM read-modify-write of O is rare.
+//
+// Precision: NTERMS = 3 is the fp32-parity mode -- Q, K, V and P are carried as fp16 (hi, lo*2^11) pairs,
+// each product is hi*hi + 2^-11 (hi*lo + lo*hi) with main and correction terms in separate TMEM
+// accumulators (see gemm_tc.cu).  NTERMS = 1: single fp16 / bf16 pass.
+// Optional key mask keep[B,Nk] (partial overlap, model/transformer.py:48-52): masked keys get -1e9.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int DK = 128;           // head dim
+constexpr int BQ = 128;           // queries per work item
+constexpr int BKV = 64;           // keys per inner tile
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;   // log2 units
+
+struct AttnParams {
+    int B, H, Nq, Nk;
+    float scale_log2;             // softmax scale * log2(e)
+    const uint8_t* keep;          // [B, Nk] or null
+    __half* O; int ldo; long long o_plane;
+    float* lse;                   // [B, H, Nq] log2-domain log-sum-exp, or null
+    int out_bf16;
+};
+
+template <int NTERMS>
+struct ACfg {
+    static constexpr int PL = NTERMS == 3 ? 2 : 1;
+    static constexpr int Q_TILE = BQ * 128;                     // [128 rows][64 elems] 16 KB
+    static constexpr int K_TILE = BKV * 128;                    // [64 keys][64 elems]   8 KB
+    static constexpr int V_TILE = DK * 128;                     // [128 d][64 keys]     16 KB
+    static constexpr int P_TILE = BQ * 128;                     // [128 rows][64 keys]  16 KB
+    static constexpr int Q_BYTES = 2 * PL * Q_TILE;             // 2 k-blocks of d_k
+    static constexpr int KV_STAGE = 2 * PL * K_TILE + PL * V_TILE;
+    static constexpr int P_BYTES = PL * P_TILE;
+    static constexpr int NSTAGE = 2;
+    static constexpr int OFF_KV = Q_BYTES;
+    static constexpr int OFF_P = OFF_KV + NSTAGE * KV_STAGE;
+    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int S_COLS = PL * BKV;                     // per S buffer: D0 | D1
+    static constexpr int O_COL0 = 2 * S_COLS;
+    static constexpr int TMEM_COLS = NTERMS == 3 ? 512 : 256;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int NTERMS, int FMT>
+__global__ void __launch_bounds__(256, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using C_ = ACfg<NTERMS>;
+    constexpr int PL = C_::PL;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
+    uint64_t* q_full = bars + 0;  uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;             // [2]
+    uint64_t* kv_empty = bars + 4;            // [2]
+    uint64_t* s_full = bars + 6;              // [2]
+    uint64_t* s_empty = bars + 8;             // [2]
+    uint64_t* p_full = bars + 10; uint64_t* p_empty = bars + 11;
+    uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqt = (p.Nq + BQ - 1) / BQ;
+    const int nkv = (p.Nk + BKV - 1) / BKV;
+    const long long items = (long long)p.B * p.H * nqt;
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV); }
+    if (warp == 1 && lane == 0) {
+        tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 128);
+        }
+        tc::mbar_init(p_full, 128); tc::mbar_init(p_empty, 1);
+        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 128);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, C_::TMEM_COLS); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (tc::elect_one()) {
+            uint32_t g = 0, w = 0;
+            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+                const int qt = (int)(it % nqt);
+                const int bh = (int)(it / nqt);
+                const int hh = bh % p.H, b = bh / p.H;
+                tc::mbar_wait(q_empty, (w & 1) ^ 1);
+                tc::mbar_expect_tx(q_full, C_::Q_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int pl = 0; pl < PL; ++pl)
+                        tc::tma_load_3d(smem + (kb * PL + pl) * C_::Q_TILE, &tmQ, q_full, hh * DK + kb * 64,
+                                        b * p.Nq + qt * BQ, pl);
+                for (int j = 0; j < nkv; ++j, ++g) {
+                    const int s = g & 1;
+                    tc::mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(&kv_full[s], C_::KV_STAGE);
+                    uint8_t* st = smem + C_::OFF_KV + s * C_::KV_STAGE;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int pl = 0; pl < PL; ++pl)
+                            tc::tma_load_3d(st + (kb * PL + pl) * C_::K_TILE, &tmK, &kv_full[s], hh * DK + kb * 64,
+                                            b * p.Nk + j * BKV, pl);
+#pragma unroll
+                    for (int pl = 0; pl < PL; ++pl)
+                        tc::tma_load_3d(st + 2 * PL * C_::K_TILE + pl * C_::V_TILE, &tmV, &kv_full[s], j * BKV,
+                                        (b * p.H + hh) * DK, pl);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc_qk = tc::umma_idesc(BQ, BKV, FMT);
+            constexpr uint32_t idesc_pv = tc::umma_idesc(BQ, DK, FMT);
+            const uint32_t q_addr = tc::smem_u32(smem);
+            const uint32_t p_addr = tc::smem_u32(smem + C_::OFF_P);
+            uint32_t g_qk = 0, g_pv = 0, w = 0;
+            auto issue_qk = [&]() {
+                const int s = g_qk & 1;
+                const uint32_t ph = (g_qk >> 1) & 1;
+                tc::mbar_wait(&kv_full[s], ph);
+                tc::mbar_wait(&s_empty[s], ph ^ 1);
+                tc::tc_fence_after();
+                const uint32_t k_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE);
+                const uint32_t d0 = tmem_base + s * C_::S_COLS, d1 = d0 + BKV;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * PL) * C_::Q_TILE);
+                    const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (kb | kk) != 0;
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        tc::umma_f16(d0, q_hi + adv, k_hi + adv, idesc_qk, acc);
+                        if (NTERMS == 3) {
+                            const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * PL + 1) * C_::Q_TILE);
+                            const uint64_t k_lo = tc::umma_desc_k_sw128(k_addr + (kb * PL + 1) * C_::K_TILE);
+                            tc::umma_f16(d1, q_hi + adv, k_lo + adv, idesc_qk, acc);
+                            tc::umma_f16(d1, q_lo + adv, k_hi + adv, idesc_qk, 1);
+                        }
+                    }
+                }
+                tc::umma_commit(&s_full[s]);
+                ++g_qk;
+            };
+            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+                tc::mbar_wait(q_full, w & 1);
+                tc::tc_fence_after();
+                issue_qk();
+                for (int j = 0; j < nkv; ++j) {
+                    if (j + 1 < nkv) issue_qk();
+                    else tc::umma_commit(q_empty);               // Q tile free once every QK^T of the item retired
+                    const int s = g_pv & 1;
+                    tc::mbar_wait(p_full, g_pv & 1);
+                    if (j == 0) tc::mbar_wait(o_empty, (w & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t v_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE + 2 * PL * C_::K_TILE);
+                    const uint32_t o0 = tmem_base + C_::O_COL0, o1 = o0 + DK;
+                    const uint64_t p_hi = tc::umma_desc_k_sw128(p_addr);
+                    const uint64_t v_hi = tc::umma_desc_k_sw128(v_addr);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (j | kk) != 0;
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        tc::umma_f16(o0, p_hi + adv, v_hi + adv, idesc_pv, acc);
+                        if (NTERMS == 3) {
+                            const uint64_t p_lo = tc::umma_desc_k_sw128(p_addr + C_::P_TILE);
+                            const uint64_t v_lo = tc::umma_desc_k_sw128(v_addr + C_::V_TILE);
+                            tc::umma_f16(o1, p_hi + adv, v_lo + adv, idesc_pv, acc);
+                            tc::umma_f16(o1, p_lo + adv, v_hi + adv, idesc_pv, 1);
+                        }
+                    }
+                    tc::umma_commit(&kv_empty[s]);               // K_j and V_j consumed
+                    tc::umma_commit(p_empty);                    // P buffer free / O safe to rescale
+                    ++g_pv;
+                }
+                tc::umma_commit(o_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================== softmax + output (thread = query row) ==============================
+        const int ew = warp - 4;
+        const int rloc = ew * 32 + lane;
+        const uint32_t lane_adr = (uint32_t)(ew * 32) << 16;
+        const int obf = p.out_bf16;
+        uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
+        uint32_t g = 0, w = 0;
+        for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+            const int qt = (int)(it % nqt);
+            const int bh = (int)(it / nqt);
+            const int hh = bh % p.H, b = bh / p.H;
+            const uint8_t* keep = p.keep ? p.keep + (size_t)b * p.Nk : nullptr;
+            float m_used = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int sb = g & 1;
+                tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
+                tc::tc_fence_after();
+                float s[BKV];
+                {
+                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr;
+#pragma unroll
+                    for (int hblk = 0; hblk < 2; ++hblk) {
+                        uint32_t r0[32];
+                        tc::tmem_ld_32x32(sa + hblk * 32, r0);
+                        if (NTERMS == 3) {
+                            uint32_t r1[32];
+                            tc::tmem_ld_32x32(sa + BKV + hblk * 32, r1);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                s[hblk * 32 + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
+                        } else {
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) s[hblk * 32 + i] = __uint_as_float(r0[i]);
+                        }
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2
+                // ---- scale, mask, row maximum ----
+                const int key0 = j * BKV;
+                float mt = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) {
+                    float x = s[i] * p.scale_log2;
+                    const int key = key0 + i;
+                    if (key >= p.Nk) x = -INFINITY;
+                    else if (keep && !keep[key]) x = -1e9f * kLog2e;
+                    s[i] = x;
+                    mt = fmaxf(mt, x);
+                }
+                float factor = 1.f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mt;
+                } else if (mt > m_used + kRescaleThreshold) {
+                    factor = exp2f(m_used - mt);
+                    m_used = mt;
+                    need = true;
+                }
+                float rs = 0.f;
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) { s[i] = exp2f(s[i] - m_used); rs += s[i]; }
+                l = l * factor + rs;
+                // ---- P buffer free (P V of the previous tile retired), also the point where O may be touched ----
+                tc::mbar_wait(p_empty, (g & 1) ^ 1);
+                if (__any_sync(0xffffffffu, need)) {
+                    tc::tc_fence_after();
+                    const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr;
+#pragma unroll 1
+                    for (int c = 0; c < PL * DK; c += 32) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32(oa + c, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+                        tmem_st_32x32(oa + c, r);
+                    }
+                    tmem_st_wait();
+                    tc::tc_fence_before();
+                }
+                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile ----
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int pos = (c ^ (rloc & 7)) * 16;
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) wv[q] = tc::pack_h2(s[c * 8 + 2 * q], s[c * 8 + 2 * q + 1], obf);
+                    *reinterpret_cast<uint4*>(p_smem + pos) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    if (NTERMS == 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            wv[q] = tc::pack_h2(tc::lo_part(s[c * 8 + 2 * q], obf), tc::lo_part(s[c * 8 + 2 * q + 1], obf), obf);
+                        *reinterpret_cast<uint4*>(p_smem + C_::P_TILE + pos) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+                tc::fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
+                tc::mbar_arrive(p_full);
+            }
+            // ---- item done: O / l -> operand-format output ----
+            tc::mbar_wait(o_full, w & 1);
+            tc::tc_fence_after();
+            const int q = qt * BQ + rloc;
+            const bool q_ok = q < p.Nq;
+            const float inv_l = 1.f / l;
+            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr;
+            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK;
+#pragma unroll 1
+            for (int c = 0; c < DK; c += 32) {
+                uint32_t r0[32];
+                float v[32];
+                tc::tmem_ld_32x32(oa + c, r0);
+                if (NTERMS == 3) {
+                    uint32_t r1[32];
+                    tc::tmem_ld_32x32(oa + DK + c, r1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
+                } else {
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * inv_l;
+                }
+                if (q_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wv[t] = tc::pack_h2(v[i + 2 * t], v[i + 2 * t + 1], obf);
+                        *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        if (NTERMS == 3) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                wv[t] = tc::pack_h2(tc::lo_part(v[i + 2 * t], obf), tc::lo_part(v[i + 2 * t + 1], obf), obf);
+                            *reinterpret_cast<uint4*>(orow + p.o_plane + c + i) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        }
+                    }
+                }
+            }
+            if (p.lse && q_ok) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
+            tc::tc_fence_before();
+            tc::mbar_arrive(o_empty);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+}
+
+template <int NTERMS, int FMT>
+int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
+    using C_ = ACfg<NTERMS>;
+    auto kern = flash_attn_tc_kernel<NTERMS, FMT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long items = (long long)p.B * p.H * ((p.Nq + BQ - 1) / BQ);
+    const int grid = (int)(items < sms ? items : sms);
+    kern<<<grid, 256, C_::SMEM, st>>>(tq, tk, tv, p);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+}  // namespace
+
+// Q: operand buffer [planes][B*Nq][ldq], head hh in columns [hh*128, hh*128+128) of the given base;
+// K: [planes][B*Nk][ldk] likewise; VT: [planes][B*H*128][ldv] with row (b*H + hh)*128 + d and Nk key columns;
+// O: [planes][B*Nq][ldo] operand-format output (same head layout as Q).  d_k must be 128.
+// mode: 0 = fp16 3-term split ("h3"), 1 = fp16, 2 = bf16.  keep: optional uint8 [B,Nk] key mask.
+// lse: optional [B,H,Nq] log2-domain log-sum-exp of the scaled scores.
+VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const void* K, int ldk, long long k_plane,
+                              const void* VT, int ldv, long long v_plane, int B, int H, int Nq, int Nk, int dk,
+                              int mode, float scale, const uint8_t* keep, void* O, int ldo, long long o_plane,
+                              float* lse, cudaStream_t stream) {
+    VCR_REQUIRE(Q && K && VT && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
+    if (dk != DK || mode < 0 || mode > 2) return VCR_ERR_UNSUPPORTED;
+    if ((ldo & 7) || (o_plane & 7)) return VCR_ERR_INVALID;
+    const int planes = mode == 0 ? 2 : 1;
+    CUtensorMap tq, tk, tv;
+    int rc = vcr_make_operand_tmap(&tq, Q, H * DK, (long long)B * Nq, ldq, q_plane, planes, BQ);
+    if (rc != VCR_OK) return rc;
+    rc = vcr_make_operand_tmap(&tk, K, H * DK, (long long)B * Nk, ldk, k_plane, planes, BKV);
+    if (rc != VCR_OK) return rc;
+    rc = vcr_make_operand_tmap(&tv, VT, Nk, (long long)B * H * DK, ldv, v_plane, planes, DK);
+    if (rc != VCR_OK) return rc;
+    AttnParams p;
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
+    p.scale_log2 = scale * kLog2e; p.keep = keep;
+    p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
+    if (mode == 0) return launch_attn<3, 0>(tq, tk, tv, p, stream);
+    if (mode == 1) return launch_attn<1, 0>(tq, tk, tv, p, stream);
+    return launch_attn<1, 1>(tq, tk, tv, p, stream);
+}

@@ -233,22 +233,36 @@ def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
         ops.gemm_tc(xkv_op, Wt["wkv"], Nk, 2 * D, D, nbo=B, a_off=(Nk, 0, 0, 0), bias=W["bkv"],
                     h=k_v, h_strides=(Nk * k_v.ld, 0), h_split=D, ht=vt, ht_strides=(D * vt.ld, 0))
     att = ops.Operand.empty(B * Nq, D, mode, dev)
-    ldS = (Nk + 3) // 4 * 4
-    per_b = h * Nq * ldS * 4 * 2
-    cb = max(1, min(B, max_ws_bytes // per_b))
-    S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
-    for b0 in range(0, B, cb):
-        nb = min(cb, B - b0)
-        ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
-                    a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S, c_strides=(h * Nq * ldS, Nq * ldS))
-        Sv = S[:nb].view(nb * h * Nq, ldS)
-        keep = None
-        if m.is_src:                                                     # partial overlap (:35-53)
-            csum = ops.colsum_softmax(Sv, Nk, nb)
-            _, keep = ops.topk_select(csum, int(Nk * m.overlap2), want_idx=False, want_mask=True)
-        P = ops.softmax_operand(Sv, Nk, mode, keep=keep, rows_per_batch=h * Nq)
-        ops.gemm_tc(P, vt.rows_view(b0 * D, nb * D), Nq, dk, Nk, nbo=nb, nbi=h, a_off=(h * Nq, Nq, 0, 0),
-                    b_off=(D, dk, 0, 0), h=att.rows_view(b0 * Nq, nb * Nq), h_strides=(Nq * att.ld, dk), h_split=dk)
+    keep = None
+    if m.is_src:
+        # partial overlap (:35-53): column sums of the unmasked probabilities pick the surviving keys.
+        # This one statistic still goes through materialised scores (chunked); the attention itself is flash.
+        ldS = (Nk + 3) // 4 * 4
+        cb = max(1, min(B, max_ws_bytes // (h * Nq * ldS * 4)))
+        S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
+        csum = torch.empty((B, Nk), dtype=_F32, device=dev)
+        for b0 in range(0, B, cb):
+            nb = min(cb, B - b0)
+            ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
+                        a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
+                        c_strides=(h * Nq * ldS, Nq * ldS))
+            csum[b0:b0 + nb] = ops.colsum_softmax(S[:nb].view(nb * h * Nq, ldS), Nk, nb)
+        _, keep = ops.topk_select(csum, int(Nk * m.overlap2), want_idx=False, want_mask=True)
+    if dk == 128 and config.flash_attention:
+        ops.flash_attn_tc(q_v, k_v, vt, att, B, h, Nq, Nk, dk, scale, keep=keep)
+    else:
+        ldS = (Nk + 3) // 4 * 4
+        cb = max(1, min(B, max_ws_bytes // (h * Nq * ldS * 4 * 2)))
+        S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
+        for b0 in range(0, B, cb):
+            nb = min(cb, B - b0)
+            ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
+                        a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
+                        c_strides=(h * Nq * ldS, Nq * ldS))
+            P = ops.softmax_operand(S[:nb].view(nb * h * Nq, ldS), Nk, mode,
+                                    keep=keep[b0:b0 + nb] if keep is not None else None, rows_per_batch=h * Nq)
+            ops.gemm_tc(P, vt.rows_view(b0 * D, nb * D), Nq, dk, Nk, nbo=nb, nbi=h, a_off=(h * Nq, Nq, 0, 0),
+                        b_off=(D, dk, 0, 0), h=att.rows_view(b0 * Nq, nb * Nq), h_strides=(Nq * att.ld, dk), h_split=dk)
     out = torch.empty((B, Nq, D), dtype=_F32, device=dev)
     ops.gemm_tc(att, Wt["wo"], B * Nq, D, D, bias=W["bo"], c=out, residual=residual)
     return out

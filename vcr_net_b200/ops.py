@@ -205,6 +205,16 @@ def gemm_tc(a: Operand, b: Operand, M, N, K, *, nbo=1, nbi=1,
         outp.planes if outp is not None else 1, _stream(a.buf)), "vcr_gemm_tc")
 
 
+def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, Nk, dk, scale, keep=None, lse=None):
+    """softmax(Q K^T * scale) V per (batch, head) on tensor cores, nothing of size Nq x Nk touches HBM."""
+    L = lib()
+    L.check(L.vcr_flash_attn_tc(q.ptr, q.ld, q.plane_stride, k.ptr, k.ld, k.plane_stride, vt.ptr, vt.ld,
+                                vt.plane_stride, B, H, Nq, Nk, dk, TC_MODES[q.mode], float(scale),
+                                keep.data_ptr() if keep is not None else None, out.ptr, out.ld, out.plane_stride,
+                                lse.data_ptr() if lse is not None else None, _stream(q.buf)), "vcr_flash_attn_tc")
+    return out
+
+
 def layernorm_operand(x: torch.Tensor, a, b, eps, mode) -> Operand:
     _chk(x, "x")
     M, D, ldx = _rows(x)
