@@ -86,3 +86,25 @@ def test_host_svd_matches_numpy():
         assert np.allclose(S, np.linalg.svd(H)[1], atol=1e-12)
         assert np.allclose(U @ np.diag(S) @ V.T, H, atol=1e-12)
         assert np.allclose(U.T @ U, np.eye(3), atol=1e-10) and np.allclose(V.T @ V, np.eye(3), atol=1e-10)
+
+
+def test_dropin_rebinds_reference_symbols():
+    """The reference's own modules end up exporting OUR hot-path classes (main.py unchanged)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not mounted on this box")
+    ref_harness._install_shims()
+    import sys
+    from vcr_net_b200 import dropin
+    import vcr_net_b200 as V
+    done = dropin.install(ref_harness.REF_ROOT)
+    import model.vcrnet_model as rvm
+    import model.lpdnet_model as rlm
+    import util.util as ru
+    assert rvm.VCRNet is V.VCRNet and rvm.vcrnetIter is V.vcrnetIter and rvm.LPDNet is V.LPDNet
+    assert rlm.LPD is V.LPD and ru.knn is V.knn and rlm.knn is V.knn
+    assert callable(rvm.testVCRNet) and rvm.testVCRNet.__module__ == "model.vcrnet_model"   # loops stay the reference's
+    assert set(done) == set(dropin.HOT_PATH)
+    for name in list(sys.modules):                    # leave no reference modules behind for other tests
+        if name in ("model", "util") or name.startswith(("model.", "util.")):
+            del sys.modules[name]
