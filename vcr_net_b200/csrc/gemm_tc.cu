@@ -28,6 +28,8 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int TILE_BYTES = 128 * 128;       // 128 rows x 128 B
+constexpr int EPI_WARPS = 8;                // two per TMEM lane quarter (column halves)
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 
 struct TcGemmParams {
     int M, N, K;
@@ -41,7 +43,6 @@ struct TcGemmParams {
     __half* HT; int ldt; long long t_plane, t_so, t_si;
     int out_planes;      // 2: write hi and lo planes, 1: hi only
     int out_bf16;        // operand-format outputs are bf16 instead of fp16 (bf16 throughput mode)
-    int debug;           // timing probes (VCR_TC_DEBUG): 1 = skip global stores, 2 = skip smem staging too
 };
 
 template <int NTERMS>
@@ -52,14 +53,14 @@ struct Cfg {
     static constexpr int ACC_COLS = NTERMS == 3 ? 2 * BN : BN;      // D0 | D1
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                  // double-buffered
     static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      4 * 32 * 32 * 4 /*epilogue transpose staging*/;
+                                      EPI_WARPS * 32 * 32 * 4 /*epilogue transpose staging*/;
 };
 
 using tc::pack_h2;
 using tc::lo_part;
 
 template <int NTERMS, int FMT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
     using C_ = Cfg<NTERMS>;
     extern __shared__ uint8_t smem_raw[];
@@ -70,7 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = bars + 2 * C_::NSTAGES;      // [2]
     uint64_t* tempty = tfull + 2;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* stage_buf = reinterpret_cast<float*>(smem + C_::NSTAGES * C_::STAGE_BYTES + 256);   // [4 warps][32][32]
+    float* stage_buf = reinterpret_cast<float*>(smem + C_::NSTAGES * C_::STAGE_BYTES + 256);   // [EPI_WARPS][32][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -84,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C_::NSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS * 32); }
         tc::fence_barrier_init();
     }
     if (warp == 2) {
@@ -159,20 +160,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
+        // ===================== epilogue: TMEM -> registers -> smem transpose -> global =====================
+        // 8 warps: warp w reads TMEM lane quarter (w % 4) and column half ((w - 4) / 4) of the 128 x 128 tile.
         // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per load).  Row-major
         // outputs are transposed through a swizzled per-warp smem tile so that each global access of the
         // warp covers whole 128-byte row segments; alpha / bias / activation / residual are applied in that
-        // coalesced layout, where a lane owns the same 4 columns for all rows (bias lives in 4 registers).
-        // The transposed operand output (V^T) is stored straight from the row-per-thread layout, where
-        // consecutive lanes are consecutive rows, i.e. already coalesced.
-        const int ew = warp - 4;                               // == warp % 4: TMEM lane quarter
+        // coalesced layout, where a lane owns the same 4 columns for all rows.  The residual rows of a chunk
+        // are requested (8 x 16 B per lane, unconditionally, rows clamped) BEFORE the TMEM load so that their
+        // DRAM latency overlaps the accumulator read instead of serialising per row.
+        // The transposed operand output (V^T) re-reads the same smem tile column-wise: a lane then owns one
+        // output column = 32 consecutive V^T elements (64 contiguous bytes per plane).
+        const int ew = warp & 3;                               // == warp % 4: TMEM lane quarter
+        const int chalf = (warp - 4) >> 2;                     // column half of the tile
         const float alpha = p.alpha, slope = p.slope;
         const int act = p.act, obf = p.out_bf16, nplanes = p.out_planes;
         const int N = p.N, M = p.M, h_split = p.h_split;
         const int ldc = p.ldc, ldr = p.ldr, ldh = p.ldh;
         const bool vecC = (ldc & 3) == 0, vecR = (ldr & 3) == 0, vecH = (ldh & 3) == 0;
-        float* stg = stage_buf + ew * (32 * 32);
+        float* stg = stage_buf + (warp - 4) * (32 * 32);
         const int c4 = lane & 7, rsub = lane >> 3;
         int it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -181,19 +186,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            tc::mbar_wait(&tfull[a], aph);
-            tc::tc_fence_after();
-            const int row = m_blk * BM + ew * 32 + lane;
+            const int row0 = m_blk * BM + ew * 32;             // first row of this warp's lane quarter
+            const int row = row0 + lane;
             const bool row_ok = row < M;
             const uint32_t tadr = tmem_base + a * C_::ACC_COLS + ((uint32_t)(ew * 32) << 16);
             float* Cz = p.C ? p.C + zo * p.c_so + zi * p.c_si : nullptr;
             const float* Rz = p.R ? p.R + zo * p.r_so + zi * p.r_si : nullptr;
             __half* Hz = p.H ? p.H + zo * p.h_so + zi * p.h_si : nullptr;
             __half* Tz = p.HT ? p.HT + zo * p.t_so + zi * p.t_si : nullptr;
+            bool waited = false;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = chalf * 64 + cc * 32;
                 const int col0 = n_blk * BN + c0;
                 if (col0 >= N) break;                          // warp-uniform
+                const int col = col0 + c4 * 4;
+                const bool want_h = Hz && col0 < h_split;
+                const bool want_t = Tz && col0 + 32 > h_split;
+                const bool rowmajor = Cz != nullptr || want_h;
+                const bool full = col0 + 32 <= N;
+                const bool fast = full && (!Cz || vecC) && (!Rz || vecR) && (!want_h || (vecH && col0 + 32 <= h_split));
+                // ---- residual rows of this chunk: all 8 requests in flight before the accumulator is read ----
+                float4 rq[8];
+                if (Rz && rowmajor && fast) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int gr = min(row0 + itr * 4 + rsub, M - 1);
+                        rq[itr] = __ldg(reinterpret_cast<const float4*>(Rz + (size_t)gr * ldr + col));
+                    }
+                }
+                if (!waited) {
+                    tc::mbar_wait(&tfull[a], aph);
+                    tc::tc_fence_after();
+                    waited = true;
+                }
                 uint32_t r0[32];
                 float v[32];
                 tc::tmem_ld_32x32(tadr + c0, r0);
@@ -208,91 +234,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
                 }
-                if (Tz && col0 + 32 > h_split) {               // warp-uniform: transposed operand output
+                const bool t_fast = want_t && full && col0 >= h_split && row0 + 32 <= M && (p.ldt & 7) == 0;
+                if (want_t && !t_fast) {                       // ragged tile: scalar transposed stores
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int col = col0 + j;
-                            if (col < N && col >= h_split) {
+                            const int cj = col0 + j;
+                            if (cj < N && cj >= h_split) {
                                 float x = alpha * v[j];
-                                if (p.bias) x += __ldg(p.bias + col);
+                                if (p.bias) x += __ldg(p.bias + cj);
                                 if (act == 1) x = leaky(x, slope);
-                                unsigned short* tt = reinterpret_cast<unsigned short*>(Tz) + (size_t)(col - h_split) * p.ldt + row;
+                                unsigned short* tt = reinterpret_cast<unsigned short*>(Tz) + (size_t)(cj - h_split) * p.ldt + row;
                                 tt[0] = (unsigned short)(pack_h2(x, 0.f, obf) & 0xffff);
                                 if (nplanes == 2) tt[p.t_plane] = (unsigned short)(pack_h2(lo_part(x, obf), 0.f, obf) & 0xffff);
                             }
                         }
                     }
                 }
-                const bool want_h = Hz && col0 < h_split;
-                if ((Cz == nullptr && !want_h) || p.debug == 2) continue;        // warp-uniform
+                if (!rowmajor && !t_fast) continue;            // warp-uniform
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
                         make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                const int col = col0 + c4 * 4;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) {
-                    if (col + 4 <= N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                    else {
-                        if (col < N) b4.x = p.bias[col];
-                        if (col + 1 < N) b4.y = p.bias[col + 1];
-                        if (col + 2 < N) b4.z = p.bias[col + 2];
+                if (t_fast) {
+                    // lane = output column col0 + lane; it gathers the 32 rows of that column (conflict-free:
+                    // for a fixed row the swizzle maps the 32 columns onto 32 distinct banks)
+                    const float bz = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
+                    float x[32];
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        float y = fmaf(alpha, stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)], bz);
+                        x[rr] = act == 1 ? leaky(y, slope) : y;
+                    }
+                    __half* tt = Tz + (size_t)(col0 + lane - h_split) * p.ldt + row0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(tt + q * 8) =
+                            make_uint4(pack_h2(x[q * 8 + 0], x[q * 8 + 1], obf), pack_h2(x[q * 8 + 2], x[q * 8 + 3], obf),
+                                       pack_h2(x[q * 8 + 4], x[q * 8 + 5], obf), pack_h2(x[q * 8 + 6], x[q * 8 + 7], obf));
+                    if (nplanes == 2) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4*>(tt + p.t_plane + q * 8) =
+                                make_uint4(pack_h2(lo_part(x[q * 8 + 0], obf), lo_part(x[q * 8 + 1], obf), obf),
+                                           pack_h2(lo_part(x[q * 8 + 2], obf), lo_part(x[q * 8 + 3], obf), obf),
+                                           pack_h2(lo_part(x[q * 8 + 4], obf), lo_part(x[q * 8 + 5], obf), obf),
+                                           pack_h2(lo_part(x[q * 8 + 6], obf), lo_part(x[q * 8 + 7], obf), obf));
                     }
                 }
-                const bool vec = col + 4 <= N;
-                if (col < N) {
+                if (rowmajor && fast) {
+                    const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr) {
                         const int rl = itr * 4 + rsub;
-                        const int grow = m_blk * BM + ew * 32 + rl;
-                        if (grow >= M) continue;
+                        const int grow = row0 + rl;
                         float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
                         x.x = fmaf(alpha, x.x, b4.x); x.y = fmaf(alpha, x.y, b4.y);
                         x.z = fmaf(alpha, x.z, b4.z); x.w = fmaf(alpha, x.w, b4.w);
                         if (act == 1) { x.x = leaky(x.x, slope); x.y = leaky(x.y, slope); x.z = leaky(x.z, slope); x.w = leaky(x.w, slope); }
-                        if (p.debug == 1) { if (x.x == 123.456f) Cz[0] = x.y; continue; }
-                        if (Rz) {
-                            const float* rr = Rz + (size_t)grow * ldr + col;
-                            if (vec && vecR) {
-                                const float4 q = __ldg(reinterpret_cast<const float4*>(rr));
-                                x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                            } else {
-                                x.x += rr[0];
-                                if (col + 1 < N) x.y += rr[1];
-                                if (col + 2 < N) x.z += rr[2];
-                                if (col + 3 < N) x.w += rr[3];
-                            }
-                        }
-                        if (Cz) {
-                            float* cc = Cz + (size_t)grow * ldc + col;
-                            if (vec && vecC) {
-                                *reinterpret_cast<float4*>(cc) = x;
-                            } else {
-                                cc[0] = x.x;
-                                if (col + 1 < N) cc[1] = x.y;
-                                if (col + 2 < N) cc[2] = x.z;
-                                if (col + 3 < N) cc[3] = x.w;
-                            }
-                        }
-                        if (want_h && col < h_split) {
-                            __half* hh = Hz + (size_t)grow * ldh + col;
-                            if (vec && col + 4 <= h_split && vecH) {
+                        if (Rz) { x.x += rq[itr].x; x.y += rq[itr].y; x.z += rq[itr].z; x.w += rq[itr].w; }
+                        if (grow < M) {
+                            if (Cz) *reinterpret_cast<float4*>(Cz + (size_t)grow * ldc + col) = x;
+                            if (want_h) {
+                                __half* hh = Hz + (size_t)grow * ldh + col;
                                 *reinterpret_cast<uint2*>(hh) = make_uint2(pack_h2(x.x, x.y, obf), pack_h2(x.z, x.w, obf));
                                 if (nplanes == 2)
                                     *reinterpret_cast<uint2*>(hh + p.h_plane) =
                                         make_uint2(pack_h2(lo_part(x.x, obf), lo_part(x.y, obf), obf),
                                                    pack_h2(lo_part(x.z, obf), lo_part(x.w, obf), obf));
-                            } else {
-                                const float ys[4] = {x.x, x.y, x.z, x.w};
-                                for (int q = 0; q < 4; ++q) {
-                                    if (col + q < N && col + q < h_split) {
-                                        reinterpret_cast<unsigned short*>(hh)[q] = (unsigned short)(pack_h2(ys[q], 0.f, obf) & 0xffff);
-                                        if (nplanes == 2)
-                                            reinterpret_cast<unsigned short*>(hh + p.h_plane)[q] =
-                                                (unsigned short)(pack_h2(lo_part(ys[q], obf), 0.f, obf) & 0xffff);
-                                    }
+                            }
+                        }
+                    }
+                } else if (rowmajor) {
+                    // ragged / unaligned chunk: element-wise guarded path
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) {
+                        if (col < N) b4.x = p.bias[col];
+                        if (col + 1 < N) b4.y = p.bias[col + 1];
+                        if (col + 2 < N) b4.z = p.bias[col + 2];
+                        if (col + 3 < N) b4.w = p.bias[col + 3];
+                    }
+                    if (col < N) {
+#pragma unroll 1
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const int rl = itr * 4 + rsub;
+                            const int grow = row0 + rl;
+                            if (grow >= M) continue;
+                            const float4 x4 = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+                            float ys[4] = {fmaf(alpha, x4.x, b4.x), fmaf(alpha, x4.y, b4.y), fmaf(alpha, x4.z, b4.z), fmaf(alpha, x4.w, b4.w)};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (col + q >= N) continue;
+                                float y = ys[q];
+                                if (act == 1) y = leaky(y, slope);
+                                if (Rz) y += Rz[(size_t)grow * ldr + col + q];
+                                if (Cz) Cz[(size_t)grow * ldc + col + q] = y;
+                                if (want_h && col + q < h_split) {
+                                    unsigned short* hh = reinterpret_cast<unsigned short*>(Hz + (size_t)grow * ldh + col + q);
+                                    hh[0] = (unsigned short)(pack_h2(y, 0.f, obf) & 0xffff);
+                                    if (nplanes == 2) hh[p.h_plane] = (unsigned short)(pack_h2(lo_part(y, obf), 0.f, obf) & 0xffff);
                                 }
                             }
                         }
@@ -300,6 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+            if (!waited) { tc::mbar_wait(&tfull[a], aph); tc::tc_fence_after(); }
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[a]);
         }
@@ -339,7 +381,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)vcr_cdiv(p.M, BM) * vcr_cdiv(p.N, BN) * p.nb_outer * p.nb_inner;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, 256, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    kern<<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
@@ -410,7 +452,6 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
     p.h_split = H ? (HT ? h_split : N) : 0;
     p.HT = reinterpret_cast<__half*>(HT); p.ldt = ldt; p.t_plane = t_plane; p.t_so = t_so; p.t_si = t_si;
     p.out_planes = out_planes; p.out_bf16 = mode == 2;
-    { const char* e = getenv("VCR_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     if (mode == 0) return launch_tc<3, 0>(tmA, tmB, p, stream);
     if (mode == 1) return launch_tc<1, 0>(tmA, tmB, p, stream);
     return launch_tc<1, 1>(tmA, tmB, p, stream);
