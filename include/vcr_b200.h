@@ -106,6 +106,12 @@ int vcr_conv3_act(const float* xyz, const float* w, const float* bias, int B, in
 int vcr_edgeconv_dg(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts,
                     const float* W2, const float* b2, float slope, float* x1, int ld1, float* x2, int ld2,
                     cudaStream_t stream);
+/* Tensor-core (tcgen05/TMEM) flavour of vcr_edgeconv_dg, same contract: the DG2 GEMM runs transposed
+ * (D[out-channel][edge]) so max-over-k is an in-thread reduction.  mode: 0 = fp16 3-term split (fp32 parity),
+ * 1 = fp16, 2 = bf16.  ldpq, ld1 multiples of 4, slope >= 0. */
+int vcr_edgeconv_dg_tc(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts,
+                       const float* W2, const float* b2, float slope, int mode, float* x1, int ld1,
+                       float* x2, int ld2, cudaStream_t stream);
 /* convSN1 + max (:130-132): out = act(max_k P[idx] + Q), C in {128,256,384,512}. */
 int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, const int* idx, int k, int N,
                    long long total_pts, int C, float slope, float* out, int ldo, cudaStream_t stream);

@@ -258,6 +258,33 @@ def test_lpdnet_slope02(precision):
     assert rel_err(nump(out).transpose(0, 2, 1), g["out_s02"]) < TOL
 
 
+@pytest.mark.parametrize("B,N,slope", [(3, 101, 0.0), (2, 1024, 0.2), (1, 21, 0.0)])
+def test_edgeconv_dg_tensor_core_vs_simt(B, N, slope):
+    """csrc/edgeconv_tc.cu (tcgen05, transposed DG2 GEMM) against the FP32 SIMT kernel and a float64 restatement
+    of model/lpdnet_model.py:122-126 on ragged point counts (tiles of 8 points)."""
+    rs = np.random.RandomState(5)
+    pq = rs.randn(B, N, 256).astype(np.float32)
+    idx = rs.randint(0, N, size=(B, N, 20)).astype(np.int32)
+    w2 = (rs.randn(128, 128) / 11.0).astype(np.float32)
+    b2 = rs.randn(128).astype(np.float32)
+    e1 = pq[np.arange(B)[:, None, None], idx, :128] + pq[:, :, None, 128:]          # fp32, as the kernels do
+    e1 = np.where(e1 >= 0, e1, e1 * np.float32(slope)).astype(np.float64)
+    want1 = e1.max(2)
+    e2 = e1 @ w2.T.astype(np.float64) + b2
+    e2 = np.where(e2 >= 0, e2, e2 * slope)
+    want2 = e2.max(2)
+    for mode, tol in (("h3", 2e-6), ("fp16", 3e-3)):
+        x1 = torch.full((B, N, 128), float("nan"), device=DEV)
+        x2 = torch.full((B, N, 128), float("nan"), device=DEV)
+        ops.edgeconv_dg_tc(cu(pq), cu(idx), cu(w2), cu(b2), slope, x1, x2, mode)
+        assert np.array_equal(nump(x1), want1.astype(np.float32))
+        assert rel_err(nump(x2), want2) < tol, mode
+    y1, y2 = torch.empty((B, N, 128), device=DEV), torch.empty((B, N, 128), device=DEV)
+    ops.edgeconv_dg(cu(pq), cu(idx), cu(w2), cu(b2), slope, y1, y2)
+    assert np.array_equal(nump(y1), want1.astype(np.float32))
+    assert rel_err(nump(y2), want2) < 2e-6
+
+
 # ---------------------------------------------------------------- Transformer -------------------------
 def test_transformer_vs_golden(net_whole, net_partial, precision):
     g = load_golden("transformer")

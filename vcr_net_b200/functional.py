@@ -89,7 +89,11 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
         idx_feat = ops.knn_topk(h2, k, token_major=True)                     # :122 (feature-space kNN)
     pq1 = ops.gemm(h2, W["dg1_w"], W["dg1_b"])                               # [B,N,256] = [P|Q]
     cat = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
-    ops.edgeconv_dg(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256])  # :123-126
+    if config.precision == "fp32":
+        ops.edgeconv_dg(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256])  # :123-126
+    else:
+        ops.edgeconv_dg_tc(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256],
+                           config.precision)
     if idx_xyz is None:
         idx_xyz = ops.knn_topk(xyz, k, token_major=False)                    # :129 (3-d kNN)
     pq3 = ops.gemm(cat[:, :, 128:256], W["sn1_w"], W["sn1_b"])               # [B,N,512] = [P3|Q3]

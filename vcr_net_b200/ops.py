@@ -284,6 +284,19 @@ def edgeconv_dg(pq: torch.Tensor, idx: torch.Tensor, w2: torch.Tensor, b2: torch
             "vcr_edgeconv_dg")
 
 
+def edgeconv_dg_tc(pq: torch.Tensor, idx: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, slope: float,
+                   x1: torch.Tensor, x2: torch.Tensor, mode: str):
+    """edgeconv_dg on tcgen05 tensor cores (csrc/edgeconv_tc.cu); mode in TC_MODES."""
+    B, N, _ = pq.shape
+    _, _, ldpq = _rows(pq)
+    _, _, ld1 = _rows(x1)
+    _, _, ld2 = _rows(x2)
+    L = lib()
+    L.check(L.vcr_edgeconv_dg_tc(pq.data_ptr(), ldpq, idx.data_ptr(), idx.shape[2], N, B * N, w2.data_ptr(),
+                                 b2.data_ptr(), float(slope), TC_MODES[mode], x1.data_ptr(), ld1, x2.data_ptr(), ld2,
+                                 _stream(pq)), "vcr_edgeconv_dg_tc")
+
+
 def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float, out: torch.Tensor):
     """out[b,n,:] = act(max_k p[b, idx[b,n,k], :] + q[b,n,:]); p, q, out are [B,N,C] row views."""
     B, N, C = p.shape
