@@ -4,7 +4,7 @@
 //
 // Work item = (batch, head, 128-query tile); persistent CTAs walk the items.  Per 64-key tile:
 //   warp 1 (one elected thread)  S = Q K_j^T          tcgen05.mma 128x64x16, S in TMEM (double-buffered)
-//   warps 4-7 (thread = query row) online softmax:    tcgen05.ld S -> exp2 -> P (fp16 hi/lo) -> smem
+//   warps 4-11 (2 threads per query row, 32 keys each) online softmax: tcgen05.ld S -> exp2 -> P (fp16 hi/lo) -> smem
 //   warp 1                        O += P V_j           tcgen05.mma 128x128x16, O stays in TMEM
 //   warp 0 (one elected thread)  TMA: Q once per item, {K_j, V^T_j} through a 2-stage ring
 // QK^T of tile j+1 is issued before P V of tile j, so the tensor core works while the softmax warps
@@ -49,7 +49,9 @@ struct ACfg {
     static constexpr int OFF_KV = Q_BYTES;
     static constexpr int OFF_P = OFF_KV + NSTAGE * KV_STAGE;
     static constexpr int OFF_BAR = OFF_P + P_BYTES;
-    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int OFF_XCH = OFF_BAR + 256;               // row max / sum exchange between the warp pair
+    static constexpr int SLACK = 768;                           // alignment slack (the dynamic smem base is 1 KB aligned in practice; checked)
+    static constexpr int SMEM = OFF_XCH + 2048 + SLACK;
     static constexpr int S_COLS = PL * BKV;                     // per S buffer: D0 | D1
     static constexpr int O_COL0 = 2 * S_COLS;
     static constexpr int TMEM_COLS = NTERMS == 3 ? 512 : 256;
@@ -66,25 +68,33 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int NTERMS, int FMT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using C_ = ACfg<NTERMS>;
     constexpr int PL = C_::PL;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    if ((int)(smem - smem_raw) > C_::SLACK) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
     uint64_t* q_full = bars + 0;  uint64_t* q_empty = bars + 1;
-    uint64_t* kv_full = bars + 2;             // [2]
-    uint64_t* kv_empty = bars + 4;            // [2]
+    uint64_t* k_full = bars + 2;              // [2]  K and V^T tiles share a smem stage but are released
+    uint64_t* k_empty = bars + 4;             // [2]  separately: K_j is free right after Q K_j^T (one tile ahead of
+    uint64_t* v_full = bars + 14;             // [2]  the softmax), V_j only after P V_j, so the K load of tile j+2
+    uint64_t* v_empty = bars + 16;            // [2]  never waits for the P V chain.
     uint64_t* s_full = bars + 6;              // [2]
     uint64_t* s_empty = bars + 8;             // [2]
     uint64_t* p_full = bars + 10; uint64_t* p_empty = bars + 11;
     uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nqt = (p.Nq + BQ - 1) / BQ;
@@ -95,11 +105,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 1 && lane == 0) {
         tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
         for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 128);
+            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
+            tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 256);
         }
-        tc::mbar_init(p_full, 128); tc::mbar_init(p_empty, 1);
-        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 128);
+        tc::mbar_init(p_full, 256); tc::mbar_init(p_empty, 1);
+        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 256);
         tc::fence_barrier_init();
     }
     if (warp == 2) { tc::tmem_alloc(tmem_slot, C_::TMEM_COLS); tc::tmem_relinquish(); }
@@ -126,18 +137,20 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                         b * p.Nq + qt * BQ, pl);
                 for (int j = 0; j < nkv; ++j, ++g) {
                     const int s = g & 1;
-                    tc::mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
-                    tc::mbar_expect_tx(&kv_full[s], C_::KV_STAGE);
                     uint8_t* st = smem + C_::OFF_KV + s * C_::KV_STAGE;
+                    tc::mbar_wait(&k_empty[s], ((g >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(&k_full[s], 2 * PL * C_::K_TILE);
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int pl = 0; pl < PL; ++pl)
-                            tc::tma_load_3d(st + (kb * PL + pl) * C_::K_TILE, &tmK, &kv_full[s], hh * DK + kb * 64,
+                            tc::tma_load_3d(st + (kb * PL + pl) * C_::K_TILE, &tmK, &k_full[s], hh * DK + kb * 64,
                                             b * p.Nk + j * BKV, pl);
+                    tc::mbar_wait(&v_empty[s], ((g >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(&v_full[s], PL * C_::V_TILE);
 #pragma unroll
                     for (int pl = 0; pl < PL; ++pl)
-                        tc::tma_load_3d(st + 2 * PL * C_::K_TILE + pl * C_::V_TILE, &tmV, &kv_full[s], j * BKV,
+                        tc::tma_load_3d(st + 2 * PL * C_::K_TILE + pl * C_::V_TILE, &tmV, &v_full[s], j * BKV,
                                         (b * p.H + hh) * DK, pl);
                 }
             }
@@ -153,7 +166,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             auto issue_qk = [&]() {
                 const int s = g_qk & 1;
                 const uint32_t ph = (g_qk >> 1) & 1;
-                tc::mbar_wait(&kv_full[s], ph);
+                tc::mbar_wait(&k_full[s], ph);
                 tc::mbar_wait(&s_empty[s], ph ^ 1);
                 tc::tc_fence_after();
                 const uint32_t k_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE);
@@ -176,6 +189,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                 }
                 tc::umma_commit(&s_full[s]);
+                tc::umma_commit(&k_empty[s]);                    // K_j consumed
                 ++g_qk;
             };
             for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
@@ -187,6 +201,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     else tc::umma_commit(q_empty);               // Q tile free once every QK^T of the item retired
                     const int s = g_pv & 1;
                     tc::mbar_wait(p_full, g_pv & 1);
+                    tc::mbar_wait(&v_full[s], (g_pv >> 1) & 1);
                     if (j == 0) tc::mbar_wait(o_empty, (w & 1) ^ 1);
                     tc::tc_fence_after();
                     const uint32_t v_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE + 2 * PL * C_::K_TILE);
@@ -205,7 +220,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                             tc::umma_f16(o1, p_lo + adv, v_hi + adv, idesc_pv, 1);
                         }
                     }
-                    tc::umma_commit(&kv_empty[s]);               // K_j and V_j consumed
+                    tc::umma_commit(&v_empty[s]);                // V_j consumed
                     tc::umma_commit(p_empty);                    // P buffer free / O safe to rescale
                     ++g_pv;
                 }
@@ -213,12 +228,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ============================== softmax + output (thread = query row) ==============================
-        const int ew = warp - 4;
-        const int rloc = ew * 32 + lane;
-        const uint32_t lane_adr = (uint32_t)(ew * 32) << 16;
+        // ============================== softmax + output ==============================
+        // 8 warps: warp w owns query rows (TMEM lanes) 32*(w%4)..+32 and key columns 32*hf..+32 of the tile
+        // (hf = (w-4)/4).  The two warps of a row quarter exchange their partial row maxima through smem
+        // (pair barrier, 64 threads) so both use the same running maximum; the partial sums l are combined
+        // once per item.  Each warp rescales / writes out its half of the O columns.
+        const int qq = warp & 3, hf = (warp - 4) >> 2;
+        const int rloc = qq * 32 + lane;
+        const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
         const int obf = p.out_bf16;
         uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
+        float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // [2 slots][2 halves][128 rows]
+        auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory"); };
         uint32_t g = 0, w = 0;
         for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
             const int qt = (int)(it % nqt);
@@ -230,75 +251,85 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const int sb = g & 1;
                 tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
                 tc::tc_fence_after();
-                float s[BKV];
+                float s[32];
                 {
-                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr;
+                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr + hf * 32;
+                    uint32_t r0[32];
+                    tc::tmem_ld_32x32(sa, r0);
+                    if (NTERMS == 3) {
+                        uint32_t r1[32];
+                        tc::tmem_ld_32x32(sa + BKV, r1);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                    for (int hblk = 0; hblk < 2; ++hblk) {
-                        uint32_t r0[32];
-                        tc::tmem_ld_32x32(sa + hblk * 32, r0);
-                        if (NTERMS == 3) {
-                            uint32_t r1[32];
-                            tc::tmem_ld_32x32(sa + BKV + hblk * 32, r1);
-                            tc::tmem_ld_wait();
+                        for (int i = 0; i < 32; ++i) s[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
+                    } else {
+                        tc::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                s[hblk * 32 + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
-                        } else {
-                            tc::tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) s[hblk * 32 + i] = __uint_as_float(r0[i]);
-                        }
+                        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
                     }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2
-                // ---- scale, mask, row maximum ----
-                const int key0 = j * BKV;
-                float mt = -INFINITY;
+                // ---- (mask,) partial row maximum ----
+                const int key0 = j * BKV + hf * 32;
+                float sc = p.scale_log2;                          // exp2(s*sc - m) below
+                if (keep != nullptr || j * BKV + BKV > p.Nk) {    // warp-uniform: ragged or masked tile
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) {
-                    float x = s[i] * p.scale_log2;
-                    const int key = key0 + i;
-                    if (key >= p.Nk) x = -INFINITY;
-                    else if (keep && !keep[key]) x = -1e9f * kLog2e;
-                    s[i] = x;
-                    mt = fmaxf(mt, x);
+                    for (int i = 0; i < 32; ++i) {
+                        float x = s[i] * sc;
+                        const int key = key0 + i;
+                        if (key >= p.Nk) x = -INFINITY;
+                        else if (keep && !keep[key]) x = -1e9f * kLog2e;
+                        s[i] = x;
+                    }
+                    sc = 1.f;
                 }
+                float mt = s[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) mt = fmaxf(mt, s[i]);
+                mt *= sc;                                         // sc > 0
+                float* slot = xch + (g & 1) * 256;
+                slot[hf * 128 + rloc] = mt;
+                pair_bar();
+                mt = fmaxf(mt, slot[(hf ^ 1) * 128 + rloc]);
                 float factor = 1.f;
                 bool need = false;
                 if (j == 0) {
                     m_used = mt;
                 } else if (mt > m_used + kRescaleThreshold) {
-                    factor = exp2f(m_used - mt);
+                    factor = ex2_approx(m_used - mt);
                     m_used = mt;
                     need = true;
                 }
-                float rs = 0.f;
+                const float neg_m = -m_used;
+                float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) { s[i] = exp2f(s[i] - m_used); rs += s[i]; }
-                l = l * factor + rs;
+                for (int i = 0; i < 32; i += 2) {
+                    s[i] = ex2_approx(fmaf(s[i], sc, neg_m));         rs0 += s[i];
+                    s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m)); rs1 += s[i + 1];
+                }
+                l = l * factor + (rs0 + rs1);
                 // ---- P buffer free (P V of the previous tile retired), also the point where O may be touched ----
                 tc::mbar_wait(p_empty, (g & 1) ^ 1);
                 if (__any_sync(0xffffffffu, need)) {
                     tc::tc_fence_after();
-                    const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr;
 #pragma unroll 1
-                    for (int c = 0; c < PL * DK; c += 32) {
+                    for (int c = 0; c < PL * 64; c += 32) {       // this warp's half of D0 (and of D1)
+                        const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + (c >= 64 ? DK - 64 : 0) + hf * 64 + c;
                         uint32_t r[32];
-                        tc::tmem_ld_32x32(oa + c, r);
+                        tc::tmem_ld_32x32(oa, r);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
-                        tmem_st_32x32(oa + c, r);
+                        tmem_st_32x32(oa, r);
                     }
                     tmem_st_wait();
                     tc::tc_fence_before();
                 }
-                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile ----
+                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: 4 x 16-byte chunks per plane ----
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int pos = (c ^ (rloc & 7)) * 16;
+                for (int c = 0; c < 4; ++c) {
+                    const int pos = ((hf * 4 + c) ^ (rloc & 7)) * 16;
                     uint32_t wv[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) wv[q] = tc::pack_h2(s[c * 8 + 2 * q], s[c * 8 + 2 * q + 1], obf);
@@ -313,16 +344,21 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tc::fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
                 tc::mbar_arrive(p_full);
             }
-            // ---- item done: O / l -> operand-format output ----
+            // ---- item done: combine the two partial sums, O / l -> operand-format output (this warp's 64 columns) ----
+            pair_bar();
+            xch[hf * 128 + rloc] = l;
+            pair_bar();
+            l += xch[(hf ^ 1) * 128 + rloc];
+            pair_bar();
             tc::mbar_wait(o_full, w & 1);
             tc::tc_fence_after();
             const int q = qt * BQ + rloc;
             const bool q_ok = q < p.Nq;
             const float inv_l = 1.f / l;
-            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr;
-            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK;
+            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + hf * 64;
+            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK + hf * 64;
 #pragma unroll 1
-            for (int c = 0; c < DK; c += 32) {
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t r0[32];
                 float v[32];
                 tc::tmem_ld_32x32(oa + c, r0);
@@ -353,7 +389,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                 }
             }
-            if (p.lse && q_ok) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
+            if (p.lse && q_ok && hf == 0) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
             tc::tc_fence_before();
             tc::mbar_arrive(o_empty);
         }
@@ -373,7 +409,7 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long items = (long long)p.B * p.H * ((p.Nq + BQ - 1) / BQ);
     const int grid = (int)(items < sms ? items : sms);
-    kern<<<grid, 256, C_::SMEM, st>>>(tq, tk, tv, p);
+    kern<<<grid, 384, C_::SMEM, st>>>(tq, tk, tv, p);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
