@@ -4,9 +4,11 @@
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
 line on rank 0.  A "step" = one pass of the hot path (vcrnetIter: LPDNet embedding of both clouds ->
 Transformer pointer -> VCP head -> SVD head, all --iter iterations) over one batch of synthetic
-ModelNet40-shaped pairs.  Workload at every N: BASELINE.json configs[0] "whole-to-whole, 1024 pts,
-batch 16" per GPU (weak scaling: each rank registers its own batch, no collective on the data
-path); `--workload partial` runs configs[1] (overlap 0.575 crops -> 768 pts, --iter 3, batch 24).
+ModelNet40-shaped pairs.  Workload at every N: BASELINE.json configs[1] "partial-to-partial eval,
+overlap 0.575 crops (768 of 1024 pts), --iter 3, batch 24" per GPU (weak scaling: each rank registers
+its own batch, no collective on the data path); `--workload whole` runs configs[0] (the reference's
+own CPU-runnable case: whole-to-whole, 1024 pts, iter 1, batch 16) and its pairs/s is also reported
+in the default line under "other_workloads".
 
   value     pairs/s with inputs resident in HBM, CUDA events per step, L2 flushed between steps
   e2e       same metric through the public module API from pinned HOST buffers (H2D + D2H timed)
@@ -37,19 +39,23 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="whole", choices=["whole", "partial"])
+    ap.add_argument("--workload", default="partial", choices=["whole", "partial", "lpd-train"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: config's)")
     ap.add_argument("--num-points", type=int, default=1024)
     ap.add_argument("--precision", default=os.environ.get("VCR_PRECISION", "h3"),
                     choices=["fp32", "h3", "fp16", "bf16"],
                     help="matrix engine: fp32 SIMT | h3 = tcgen05 3-term fp16 split (fp32 parity) | fp16 | bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    ap.add_argument("--no-other-workloads", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU sample (default: 6 partial / 12 whole)")
     return ap.parse_args()
 
 
 def workload_cfg(a):
     from oracle import synth
+    if a.workload == "lpd-train":
+        return dict(name="LPDNet pre-train forward+backward (LPD loss), index-aligned pairs, 1024 pts",
+                    partial=False, iters=1, batch=a.batch or 16, overlap2=0.75, reserve=1.0, train=True)
     if a.workload == "whole":
         return dict(name="VCR-Net whole-to-whole eval, synthetic ModelNet40-shaped pairs, 1024 pts, iter=1",
                     partial=False, iters=1, batch=a.batch or 16, overlap2=0.75, reserve=1.0)
@@ -86,7 +92,7 @@ def run_reference_arm(a, cfg, rank, world):
     if rank != 0:
         return
     times = []
-    n = a.cpu_sample_pairs
+    n = 2                                   # bounded per-step sample so K + W steps end within minutes
     for i in range(a.warmup + a.steps):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, n)
         if i >= a.warmup:
@@ -98,7 +104,9 @@ def run_reference_arm(a, cfg, rank, world):
         "impl": "reference", "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "batch_per_step": n, "num_points": a.num_points},
+        "config": {"workload": cfg["name"], "batch_per_gpu": n, "num_points": a.num_points, "iter": cfg["iters"],
+                   "precision": "fp32 (numpy)", "parallelism": "host cores of rank 0 only",
+                   "note": "bounded sample: 2 pairs per step instead of the GPU arm's batch"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{n} pairs per step through oracle/vcr_oracle.py (numpy restatement of the "
                                    f"reference; the reference is Python/torch and cannot travel to this box)"},
@@ -161,68 +169,73 @@ def gemm_flops(args):
     return 2.0 * M * N * K * nbo * nbi
 
 
-def run_gpu_arm(a, cfg, rank, world, local_rank):
+def measure(a, cfg, rank, world, dev, local_rank, steps, warmup, profile=True):
+    """Time `steps` steps of one workload on this rank's GPU.  Returns per-rank sums (ms) and the per-call profile."""
     import torch
     import torch.distributed as dist
     import vcr_net_b200 as V
     from vcr_net_b200._lib import lib
     from oracle import synth
     from oracle.ref_harness import default_args
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=b200) needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from vcr_net_b200 import config as vcfg
-    vcfg.set_precision(a.precision)
     L = lib()
     ckpt = load_ckpt()
-    net = V.VCRNet(default_args(partial=cfg["partial"], overlap2=cfg["overlap2"])).to(dev).eval()
-    net.load_state_dict(synth.checkpoint_to_torch(ckpt), strict=True)
+    train = bool(cfg.get("train"))
+    if train:          # BASELINE config 3: LPD(args) forward + loss + backward (model/lpdnet_model.py:140-229)
+        net = V.LPD(default_args(model="lpd", num_points=a.num_points)).to(dev).train()
+        lpd = np.load(os.path.join(ROOT, "tests", "golden", "lpd_pretrained_weights.npz"))
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in lpd.items()}, strict=True)
+    else:
+        net = V.VCRNet(default_args(partial=cfg["partial"], overlap2=cfg["overlap2"])).to(dev).eval()
+        net.load_state_dict(synth.checkpoint_to_torch(ckpt), strict=True)
     B = cfg["batch"]
     # each rank registers its own pairs (weak scaling; items rank*B .. rank*B+B-1), a few distinct batches
     nbatches = 2
     host = []
     for j in range(nbatches):
         p = synth.make_pairs(B, a.num_points, partial=cfg["partial"], reserve=cfg["reserve"] if cfg["partial"] else 1.0,
-                             first_item=(rank * nbatches + j) * B)
+                             first_item=(rank * nbatches + j) * B, aligned=train)
         host.append((torch.from_numpy(p["src"]).pin_memory(), torch.from_numpy(p["tgt"]).pin_memory()))
     devb = [(s.to(dev), t.to(dev)) for s, t in host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def step(i):
-        s, t = devb[i % nbatches]
+    def run(s, t):
+        if train:
+            net.zero_grad(set_to_none=True)
+            out = net(s, t)
+            out[2].backward()
+            return out
         return V.vcrnetIter(net, s, t, iter=cfg["iters"])
+
+    def step(i):
+        return run(*devb[i % nbatches])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for i in range(a.warmup):
+    res = {"B": B, "M": int(devb[0][0].shape[2])}
+    with (torch.enable_grad() if train else torch.no_grad()):
+        for i in range(warmup):
             step(i)
         barrier()
         clocks = Clocks(local_rank)
         clocks.start()
         # ---- device-resident timing -------------------------------------------------------------
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         l0 = L.vcr_launch_count()
         barrier()
         t_wall0 = time.perf_counter()
-        for i in range(a.steps):
+        for i in range(steps):
             flush.fill_(float(i))                     # L2 flush, outside the per-step event bracket
             ev[i][0].record(stream)
             step(i)
             ev[i][1].record(stream)
         barrier()
-        t_wall = time.perf_counter() - t_wall0
-        launches = L.vcr_launch_count() - l0
-        ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
-        ms_total = sum(ms_steps)
+        res["wall_s"] = time.perf_counter() - t_wall0
+        res["launches"] = L.vcr_launch_count() - l0
+        res["ms_total"] = sum(e0.elapsed_time(e1) for e0, e1 in ev)
         # ---- end-to-end: pinned host -> device -> path -> host, through the module API -------------
         R_host = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
         t_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
@@ -232,47 +245,103 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
             hs, ht = host[i % nbatches]
             sbuf.copy_(hs, non_blocking=True)
             tbuf.copy_(ht, non_blocking=True)
-            out = V.vcrnetIter(net, sbuf, tbuf, iter=cfg["iters"])
-            R_host.copy_(out[2], non_blocking=True)
-            t_host.copy_(out[3], non_blocking=True)
+            out = run(sbuf, tbuf)
+            if train:
+                t_host[0, :1].copy_(out[2].detach().reshape(1), non_blocking=True)       # the loss
+            else:
+                R_host.copy_(out[2], non_blocking=True)
+                t_host.copy_(out[3], non_blocking=True)
 
         for i in range(2):
             e2e_step(i)
         barrier()
-        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-        for i in range(a.steps):
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
             flush.fill_(float(i))
             ee[i][0].record(stream)
             e2e_step(i)
             ee[i][1].record(stream)
         barrier()
-        ms_e2e = sum(e0.elapsed_time(e1) for e0, e1 in ee)
-        clk = clocks.stop()
+        res["ms_e2e"] = sum(e0.elapsed_time(e1) for e0, e1 in ee)
+        res["clocks"] = clocks.stop()
         # ---- per-kernel CUDA-event profile of the same step (roofline leg) --------------------------
-        L.profile_begin()
-        nprof = 3
-        for i in range(nprof):
-            flush.fill_(1.0)
-            step(i)
-        prof = L.profile_end()
+        res["prof"], res["nprof"] = [], 3
+        if profile:
+            L.profile_begin()
+            for i in range(res["nprof"]):
+                flush.fill_(1.0)
+                step(i)
+            res["prof"] = L.profile_end()
+    del net, devb, flush
+    return res
 
-    # max over ranks
+
+def reduce_max(world, dev, *vals):
+    if world == 1:
+        return vals
+    import torch
+    import torch.distributed as dist
+    tt = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return tuple(float(x) for x in tt)
+
+
+def ncu_evidence(kernel):
+    """DRAM traffic / pipe activity of `kernel` from the committed `ncu --set full` capture (profiles/*_ncu_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1])).get(kernel)
+        if d:
+            d = dict(d, file=os.path.relpath(files[-1], ROOT))
+        return d
+    except Exception:
+        return None
+
+
+def run_gpu_arm(a, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=b200) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+        dist.init_process_group("nccl", device_id=dev)
+    from vcr_net_b200 import config as vcfg
+    vcfg.set_precision(a.precision)
+
+    r = measure(a, cfg, rank, world, dev, local_rank, a.steps, a.warmup)
+    ms_total, ms_e2e = reduce_max(world, dev, r["ms_total"], r["ms_e2e"])
+    launches = r["launches"]
+    if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt[0])
+    # the other parity config, short, for context (same timing rules)
+    other = None
+    if a.workload == "partial" and not a.no_other_workloads:
+        a2 = argparse.Namespace(**vars(a))
+        a2.workload, a2.batch = "whole", 0
+        cfg2 = workload_cfg(a2)
+        steps2 = max(5, a.steps // 2)
+        r2 = measure(a2, cfg2, rank, world, dev, local_rank, steps2, 3, profile=False)
+        m2, e2 = reduce_max(world, dev, r2["ms_total"], r2["ms_e2e"])
+        other = {cfg2["name"]: {"value": r2["B"] * steps2 * world / (m2 / 1e3), "unit": "pairs/s",
+                                "e2e": r2["B"] * steps2 * world / (e2 / 1e3), "batch_per_gpu": r2["B"],
+                                "ms_per_step": m2 / steps2, "steps": steps2}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    B, M, prof, nprof, clk, t_wall = r["B"], r["M"], r["prof"], r["nprof"], r["clocks"], r["wall_s"]
     pairs_total = B * a.steps * world
     value = pairs_total / (ms_total / 1e3)
     e2e_value = pairs_total / (ms_e2e / 1e3)
-    M = devb[0][0].shape[2]
 
     # roofline: aggregate per C-ABI entry point
     agg = {}
@@ -288,15 +357,22 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     except Exception:
         pass
     step_ms_prof = sum(d["ms"] for d in agg.values()) / nprof
+    ev = ncu_evidence(top[0])
     roof = {"kernel": top[0], "launches_per_step": top[1]["n"] / nprof, "share_of_step": top[1]["ms"] / nprof / step_ms_prof,
-            "avg_launch_ms": top[1]["ms"] / top[1]["n"], "traffic": None}
+            "avg_launch_ms": top[1]["ms"] / top[1]["n"],
+            "traffic": ev["mean_dram_bytes_per_launch"] if ev else None}
+    if ev:
+        roof["ncu"] = ev
     if top[1]["flops"] > 0:
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12
+        passes = 3 if (a.precision == "h3" and top[0] == "vcr_gemm_tc") else 1
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
+                    tensor_passes_per_product=passes, tensor_work_frac=passes * ach / peak,
                     note=("fp32 SIMT FFMA kernel measured against the dense bf16 tensor peak" if top[0] == "vcr_gemm_f32"
-                          else "algorithmic 2MNK flops; the h3 parity mode spends 3 fp16 tensor passes per product"
+                          else "achieved = algorithmic 2MNK flops / CUDA-event launch time; the h3 parity mode issues 3 fp16 "
+                               "tensor passes per product, so the tensor pipe does tensor_work_frac of the measured bf16 peak"
                           if a.precision == "h3" else "single tensor pass"))
     else:
         roof.update(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs", 6650.0), unit="GB/s", frac=None)
@@ -319,11 +395,14 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         "kernel_ms_per_step": breakdown,
         "wall_s_timed_region": t_wall,
     }
-    if not a.no_cpu_baseline:
+    if other:
+        line["other_workloads"] = other
+    if not a.no_cpu_baseline and not cfg.get("train"):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, a.cpu_sample_pairs)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{a.cpu_sample_pairs} pairs of the same workload, one pass of "
-                                          f"oracle/vcr_oracle.py (numpy), {dt:.1f} s"}
+                                          f"oracle/vcr_oracle.py (numpy restatement of the reference, BLAS threads = all "
+                                          f"{os.cpu_count()} cores), {dt:.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -340,6 +419,8 @@ def main():
                                   f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                   str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
     cfg = workload_cfg(a)
+    if a.cpu_sample_pairs <= 0:
+        a.cpu_sample_pairs = 6 if cfg["partial"] else 12
     if a.impl == "reference":
         run_reference_arm(a, cfg, rank, world)
     else:

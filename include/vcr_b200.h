@@ -178,6 +178,31 @@ int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, 
                   long long stride_in, long long stride_out, cudaStream_t stream);
 int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 
+/* ---- LPDNet backward (BASELINE config 3: LPD pre-training forward + backward) ------------------------
+ * The reference differentiates model/lpdnet_model.py:103-137 with autograd (loss at :149-229, optimiser step in
+ * train_one_epoch :232-276).  These are the gradient kernels of the factored forward (csrc/train.cu); the dense
+ * data-gradient products reuse vcr_gemm_f32 with b_layout = 1.
+ * vcr_wgrad_f32: dW[N,K] += G[M,N]^T X[M,K], db[N] += column sums of G (db may be NULL); caller zero-initialises. */
+int vcr_wgrad_f32(const float* G, int ldg, const float* X, int ldx, long long M, int N, int K, float* dW,
+                  int lddw, float* db, cudaStream_t stream);
+/* gz = gy * LeakyReLU'(z) from the saved post-activation y (F.leaky_relu backward). */
+int vcr_act_bwd(const float* gy, int ldg, const float* y, int ldy, long long rows, int cols, float slope,
+                float* gz, int ldz, cudaStream_t stream);
+/* backward of vcr_gather_max (convSN1 + max over k, :130-132): gQ written, gP accumulated (zero-initialised). */
+int vcr_gather_max_bwd(const float* P, int ldp, const float* Q, int ldq, const int* idx, int k, int N,
+                       long long total_pts, int C, float slope, const float* gout, int ldgo, float* gP,
+                       int ldgp, float* gQ, int ldgq, cudaStream_t stream);
+/* e1[pt,kk,:] = act(P[nbr] + Q[pt]) with PQ = [P | Q] rows of 2C floats (convDG1 output, :123), E is [T*k, C]. */
+int vcr_edge_gather_act(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts, int C,
+                        float slope, float* E, cudaStream_t stream);
+/* Z [T,k,C] = convDG2 pre-activations in, g_Z out: g_x2 routed to the arg-max edge per (point, channel) (:125-126). */
+int vcr_edge_max_bwd(float* Z, const float* gx, int ldgx, int k, long long total_pts, int C, float slope,
+                     cudaStream_t stream);
+/* g_e1 (+ g_x1 on the arg-max edge, :124) -> gPQ = [gP | gQ] rows of 2C floats (gP accumulated, zero-initialised). */
+int vcr_edge_bwd_scatter(const float* E, const float* gE, const float* gx1, int ldgx, const int* idx, int k,
+                         int N, long long total_pts, int C, float slope, float* gPQ, int ldg,
+                         cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

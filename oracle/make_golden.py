@@ -173,6 +173,53 @@ def main():
         save("lpd_loss", src=pa["src"], tgt=pa["tgt"], loss=N_(loss), mse=N_(mse), mae=N_(mae),
              src_emb=N_(se_l))
 
+    make_lpd_train(ref, lpd_sd)
+
+
+def make_lpd_train(ref=None, lpd_sd=None):
+    """BASELINE config 3 pin (LPD pre-training forward + backward, model/lpdnet_model.py:149-229 under autograd):
+    parameter gradients of (a) a fixed linear functional of the LPDNet embedding and (b) the LPD loss, from the live
+    reference, together with the neighbour sets the reference used (so a test can inject them)."""
+    torch.set_num_threads(1)
+    if ref is None:
+        ref = ref_harness.import_reference()
+        lpd_sd = torch.load(os.path.join(ref_harness.REF_ROOT, "pretrained", "lpd-pretrained.t7"),
+                            map_location="cpu", weights_only=True)
+    U, LP = ref.util, ref.lpdnet_model
+    pa = synth.make_pairs(2, 256, aligned=True, first_item=60)
+    largs = ref_harness.default_args(model="lpd", num_points=256)
+    lnet = LP.LPD(largs).train()
+    lnet.load_state_dict(lpd_sd, strict=True)
+    emb = lnet.emb_nn
+    both = T(np.concatenate([pa["src"], pa["tgt"]], axis=0))               # [4,3,256]
+    with torch.no_grad():
+        h = F.leaky_relu(emb.conv2_lpd(F.leaky_relu(emb.conv1_lpd(both), 0.2)), 0.2)
+        idx_feat = U.knn(h, 20)
+        idx_xyz = U.knn(both, 20)
+    # (a) LPDNet level: L = sum(emb(x) * Rw)
+    rng = np.random.RandomState(7)
+    Rw = rng.standard_normal((4, 512, 256)).astype(np.float32)
+    lnet.zero_grad()
+    out = emb(both)
+    # The pre-trained conv3_lpd has dead output channels (|weights| ~ 1e-11) whose pre-activations are ~1e-10: the
+    # sign there, hence LeakyReLU', is summation-order noise.  The functional is supported away from that kink.
+    keep = (out.detach().abs() > 1e-6)
+    Rw = Rw * N_(keep).astype(np.float32)
+    (out * T(Rw)).sum().backward()
+    ga = {"ga." + k: N_(p.grad).copy() for k, p in emb.named_parameters()}
+    # (b) LPD level: the pre-training loss
+    lnet.zero_grad()
+    se, te, loss, mse, mae = lnet(T(pa["src"]), T(pa["tgt"]))
+    loss.backward()
+    gb = {"gb." + k: N_(p.grad).copy() for k, p in emb.named_parameters()}
+    # Rw is reproducible from RandomState(7); the embedding is stored subsampled (every 16th point)
+    save("lpd_train", src=pa["src"], tgt=pa["tgt"], idx_feat=N_(idx_feat).astype(np.int32),
+         idx_xyz=N_(idx_xyz).astype(np.int32), emb_sub=N_(out)[:, :, ::16].copy(),
+         Rw_keep_bits=np.packbits(N_(keep).reshape(-1)), loss=N_(loss), mse=N_(mse), mae=N_(mae), **ga, **gb)
+
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
+        make_lpd_train()
+    else:
+        main()

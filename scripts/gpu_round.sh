@@ -1,21 +1,24 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench (both workloads), per-call profile, ncu launch list + full-set capture.
+# One GPU-box pass: parity tests, bench (default = configs[1] partial; + whole / lpd-train / fp16), per-call profile,
+# and (unless "nonc") the ncu launch list + full-set capture of the top kernels.
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 3 --workload whole > gpurun_out/bench_whole_h3.json 2> gpurun_out/bench_whole_h3.err
+tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+timeout 600 python bench.py --steps 20 --warmup 3 --workload whole --no-cpu-baseline > gpurun_out/bench_whole_h3.json 2> gpurun_out/bench_whole_h3.err
 cat gpurun_out/bench_whole_h3.json
-timeout 600 python bench.py --steps 10 --warmup 3 --workload partial --no-cpu-baseline > gpurun_out/bench_partial_h3.json 2> gpurun_out/bench_partial_h3.err
-cat gpurun_out/bench_partial_h3.json
 timeout 600 python bench.py --steps 20 --warmup 3 --workload whole --precision fp16 --no-cpu-baseline > gpurun_out/bench_whole_fp16.json 2> gpurun_out/bench_whole_fp16.err
+timeout 600 python bench.py --steps 5 --warmup 3 --workload lpd-train > gpurun_out/bench_lpd_train.json 2> gpurun_out/bench_lpd_train.err
+cat gpurun_out/bench_lpd_train.json; tail -3 gpurun_out/bench_lpd_train.err
 timeout 300 python scripts/step_profile.py h3 > gpurun_out/step_profile_h3.txt 2>&1
 cat gpurun_out/step_profile_h3.txt
 timeout 300 python scripts/step_profile.py h3 partial > gpurun_out/step_profile_partial_h3.txt 2>&1
 if [ "$1" != "nonc" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_h3.csv \
-    python bench.py --steps 2 --warmup 1 --workload whole --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_h3.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_launch.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_h3.csv > gpurun_out/launches_h3_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|flash_attn|knn_topk|edgeconv_dg_tc' -s 40 -c 16 \
-    -f -o gpurun_out/prof_h3 python bench.py --steps 1 --warmup 1 --workload whole --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|flash_attn|knn_select|edgeconv_dg_tc' -s 60 -c 24 \
+    -f -o gpurun_out/prof_h3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_full.log 2>&1
 fi

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vcr_net_b200.shard import gather_results, shard_batch, shard_bounds
+from vcr_net_b200.shard import allreduce_gradients, gather_results, shard_batch, shard_bounds
 
 
 def _free_port():
@@ -50,3 +50,31 @@ def test_two_rank_gloo_gather(tmp_path):
     src = torch.arange(n_items * 3 * 5, dtype=torch.float32).reshape(n_items, 3, 5)
     want = (src.sum(dim=2) * 2.0 + 1.0).numpy()
     assert np.array_equal(np.load(out), want)
+
+
+def _grad_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))     # same init on every rank
+    x = torch.arange(8 * 5, dtype=torch.float32).reshape(8, 5) / 10.0
+    (mine,) = shard_batch([x], world, rank)
+    net(mine).pow(2).sum().backward()                                           # per-rank gradient of its shard
+    n = allreduce_gradients(net, average=False)
+    if rank == 0:
+        np.save(out_path, torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy())
+        assert n == sum(p.numel() for p in net.parameters())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce(tmp_path):
+    """Sum of per-shard gradients over 2 ranks == gradient of the unsharded batch (training all-reduce)."""
+    out = str(tmp_path / "grad.npy")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))
+    x = torch.arange(8 * 5, dtype=torch.float32).reshape(8, 5) / 10.0
+    net(x).pow(2).sum().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy()
+    assert np.allclose(np.load(out), want, rtol=1e-5, atol=1e-6)

@@ -107,8 +107,93 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
         ops.gemm_tc(ops.to_operand(cat, mode), w3, B * N, W["w3"].shape[0], 512, bias=W["b3"], act=1,
                     slope=slope, c=emb)
     if stages is not None:
-        stages.update(f64=h2, idx_feat=idx_feat, idx_xyz=idx_xyz, cat=cat)
+        stages.update(f64=h2, idx_feat=idx_feat, idx_xyz=idx_xyz, cat=cat, h1=h1, pq1=pq1, pq3=pq3)
     return emb
+
+
+class LPDNetTrainFn(torch.autograd.Function):
+    """LPDNet.forward with a hand-written backward (BASELINE config 3; the reference differentiates
+    model/lpdnet_model.py:103-137 with autograd).  Forward = lpdnet_tokens; backward = csrc/train.cu kernels +
+    vcr_gemm_f32 data-gradient products, fp32 throughout.  Gradients flow to the 12 parameters only (the input
+    cloud and the kNN indices carry none, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, m, xyz, idx_feat, idx_xyz, *params):
+        st = {}
+        with torch.no_grad():
+            emb = lpdnet_tokens(m, xyz, idx_feat=idx_feat, idx_xyz=idx_xyz, stages=st)
+            xyz_t = ops.transpose_batched(xyz.contiguous())                  # [B,N,3]
+        ctx.m = m
+        ctx.st = st
+        ctx.saved = (xyz_t, emb)
+        return emb
+
+    @staticmethod
+    def backward(ctx, g_emb):
+        m, st = ctx.m, ctx.st
+        xyz_t, emb = ctx.saved
+        W = lpdnet_weights(m)
+        slope = float(m.negative_slope)
+        k = m.k
+        h1, h2, pq1, cat, pq3 = st["h1"], st["f64"], st["pq1"], st["cat"], st["pq3"]
+        idx_f, idx_x = st["idx_feat"], st["idx_xyz"]
+        B, N, _ = emb.shape
+        T = B * N
+        g_emb = g_emb.contiguous()
+        # conv3_lpd (:134-135)
+        g_z3 = ops.act_bwd(g_emb.view(T, -1), emb.view(T, -1), slope)
+        gW3, gb3 = ops.wgrad(g_z3, cat.view(T, 512))
+        g_cat = ops.gemm(g_z3, W["w3"], b_layout=1).view(B, N, 512)
+        # convSN1 + max (:130-132)
+        g_pq3 = torch.zeros((B, N, 512), dtype=_F32, device=emb.device)
+        ops.gather_max_bwd(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_x, slope, g_cat[:, :, 256:512],
+                           g_pq3[:, :, 0:256], g_pq3[:, :, 256:512])
+        gWsn, gbsn = ops.wgrad(g_pq3.view(T, 512), cat[:, :, 128:256])
+        g_x2 = ops.gemm(g_pq3.view(T, 512), W["sn1_w"], b_layout=1, residual=g_cat[:, :, 128:256]).view(B, N, 128)
+        # convDG2 + max (:125-126), convDG1 + max (:123-124)
+        e1 = ops.edge_gather_act(pq1, idx_f, slope)                            # [T*k,128]
+        z2 = ops.gemm(e1, W["dg2_w"], W["dg2_b"])
+        ops.edge_max_bwd_(z2, g_x2, k, slope)                                  # z2 <- g_z2
+        gWdg2, gbdg2 = ops.wgrad(z2, e1)
+        g_e1 = ops.gemm(z2, W["dg2_w"], b_layout=1)
+        g_pq1 = ops.edge_bwd_scatter(e1, g_e1, g_cat[:, :, 0:128], idx_f, slope)
+        del e1, z2, g_e1
+        gWdg1, gbdg1 = ops.wgrad(g_pq1.view(T, 256), h2.view(T, 64))
+        g_h2 = ops.gemm(g_pq1.view(T, 256), W["dg1_w"], b_layout=1)
+        # conv2_lpd, conv1_lpd (:111-112)
+        g_z2 = ops.act_bwd(g_h2, h2.view(T, 64), slope)
+        gW2, gb2 = ops.wgrad(g_z2, h1.view(T, 64))
+        g_h1 = ops.gemm(g_z2, W["w2"], b_layout=1)
+        g_z1 = ops.act_bwd(g_h1, h1.view(T, 64), slope)
+        gW1, gb1 = ops.wgrad(g_z1, xyz_t.view(T, 3))
+
+        def unsplit(gw, gb, conv):
+            co = conv.weight.shape[0]
+            return (torch.cat([gw[:co], gw[co:]], dim=1).reshape(conv.weight.shape), gb[co:].clone())
+
+        gdg1_w, gdg1_b = unsplit(gWdg1, gbdg1, m.convDG1[0])
+        gsn_w, gsn_b = unsplit(gWsn, gbsn, m.convSN1[0])
+        grads = {
+            "conv1_lpd.weight": gW1.reshape(m.conv1_lpd.weight.shape), "conv1_lpd.bias": gb1,
+            "conv2_lpd.weight": gW2.reshape(m.conv2_lpd.weight.shape), "conv2_lpd.bias": gb2,
+            "conv3_lpd.weight": gW3.reshape(m.conv3_lpd.weight.shape), "conv3_lpd.bias": gb3,
+            "convDG1.0.weight": gdg1_w, "convDG1.0.bias": gdg1_b,
+            "convDG2.0.weight": gWdg2.reshape(m.convDG2[0].weight.shape), "convDG2.0.bias": gbdg2,
+            "convSN1.0.weight": gsn_w, "convSN1.0.bias": gsn_b,
+        }
+        ctx.st = None
+        return (None, None, None, None) + tuple(grads[n] for n in LPDNET_PARAM_ORDER)
+
+
+LPDNET_PARAM_ORDER = ("conv1_lpd.weight", "conv1_lpd.bias", "conv2_lpd.weight", "conv2_lpd.bias",
+                      "conv3_lpd.weight", "conv3_lpd.bias", "convDG1.0.weight", "convDG1.0.bias",
+                      "convDG2.0.weight", "convDG2.0.bias", "convSN1.0.weight", "convSN1.0.bias")
+
+
+def lpdnet_tokens_train(m, xyz, idx_feat=None, idx_xyz=None):
+    """Differentiable lpdnet_tokens (w.r.t. the module's parameters)."""
+    named = dict(m.named_parameters())
+    return LPDNetTrainFn.apply(m, xyz, idx_feat, idx_xyz, *[named[n] for n in LPDNET_PARAM_ORDER])
 
 
 # --------------------------------------------------------------------------------------------------

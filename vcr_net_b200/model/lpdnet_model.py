@@ -35,10 +35,16 @@ class LPDNet(nn.Module):
 
     def forward_tokens(self, x, idx_feat=None, idx_xyz=None, stages=None):
         """x [B,3,N] -> tokens [B,N,emb_dims] (internal fast path, no output transpose)."""
+        if stages is None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return Fn.lpdnet_tokens_train(self, x, idx_feat=idx_feat, idx_xyz=idx_xyz)     # training: custom backward
         return Fn.lpdnet_tokens(self, x, idx_feat=idx_feat, idx_xyz=idx_xyz, stages=stages)
 
-    def forward(self, x):
-        return ops.transpose_batched(self.forward_tokens(x))
+    def forward(self, x, idx_feat=None, idx_xyz=None):
+        """idx_feat / idx_xyz (int32 [B,N,20], optional) inject neighbour sets like get_graph_feature(x, idx=...)."""
+        tok = self.forward_tokens(x, idx_feat=idx_feat, idx_xyz=idx_xyz)
+        if tok.requires_grad:
+            return tok.transpose(1, 2).contiguous()   # autograd-visible; values identical to the kernel transpose
+        return ops.transpose_batched(tok)
 
 
 class LPD(nn.Module):

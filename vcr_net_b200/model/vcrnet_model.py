@@ -106,6 +106,7 @@ class VCRNet(nn.Module):
             raise Exception("Not implemented")            # att / dist heads: SURVEY.md section 8(f)
         self.svd = SVDHead(args=args)
 
+    @torch.no_grad()      # registration INFERENCE path: only the LPD pre-training path (LPD / LPDNet) has a backward
     def forward(self, *input, stages=None):
         src, tgt = input[0].contiguous(), input[1].contiguous()
         B = src.shape[0]

@@ -97,12 +97,15 @@ def fps(xyz: torch.Tensor, npoint: int, want64: bool = True):
 # --------------------------------------------------------------------------------------------------
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None, act: int = 0,
-         slope: float = 0.0, alpha: float = 1.0):
+         slope: float = 0.0, alpha: float = 1.0, b_layout: int = 0):
     """out[M,N] = act(alpha * a[M,K] @ w[N,K]^T + bias) + residual.  a/out/residual may be strided
-    row views (last dim contiguous)."""
+    row views (last dim contiguous).  b_layout=1: w is stored [K,N] (out = a @ w, the data-gradient product)."""
     _chk(a, "a"); _chk(w, "w")
     M, K, lda = _rows(a)
-    N, K2, ldb = _rows(w)
+    if b_layout == 0:
+        N, K2, ldb = _rows(w)
+    else:
+        K2, N, ldb = _rows(w)
     assert K == K2, (K, K2)
     if out is None:
         out = torch.empty(a.shape[:-1] + (N,), dtype=_F32, device=a.device)
@@ -113,7 +116,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, *, out=None, residual=None
         Mr, Nr, ldr = _rows(residual)
         assert (Mr, Nr) == (M, N)
     L = lib()
-    L.check(L.vcr_gemm_f32(a.data_ptr(), lda, 0, 0, w.data_ptr(), ldb, 0, 0, 0,
+    L.check(L.vcr_gemm_f32(a.data_ptr(), lda, 0, 0, w.data_ptr(), ldb, 0, 0, int(b_layout),
                            out.data_ptr(), ldc, 0, 0,
                            bias.data_ptr() if bias is not None else None,
                            residual.data_ptr() if residual is not None else None, ldr, 0, 0,
@@ -306,6 +309,85 @@ def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float
     L = lib()
     L.check(L.vcr_gather_max(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), idx.shape[2], N, B * N, C,
                              float(slope), out.data_ptr(), ldo, _stream(p)), "vcr_gather_max")
+
+
+# --------------------------------------------------------------------------------------------------
+# LPDNet backward pieces (csrc/train.cu)
+# --------------------------------------------------------------------------------------------------
+
+def wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+    """g [M,N], x [M,K] row views -> (dW [N,K] = g^T x, db [N] = column sums of g)."""
+    _chk(g, "g"); _chk(x, "x")
+    M, N, ldg = _rows(g)
+    M2, K, ldx = _rows(x)
+    assert M == M2, (M, M2)
+    dW = torch.zeros((N, K), dtype=_F32, device=g.device)
+    db = torch.zeros((N,), dtype=_F32, device=g.device) if want_bias else None
+    L = lib()
+    L.check(L.vcr_wgrad_f32(g.data_ptr(), ldg, x.data_ptr(), ldx, M, N, K, dW.data_ptr(), K,
+                            db.data_ptr() if want_bias else None, _stream(g)), "vcr_wgrad_f32")
+    return dW, db
+
+
+def act_bwd(gy: torch.Tensor, y: torch.Tensor, slope: float):
+    """gz = gy * LeakyReLU'(z), y = the saved post-activation output (row views)."""
+    _chk(gy, "gy"); _chk(y, "y")
+    M, N, ldg = _rows(gy)
+    M2, N2, ldy = _rows(y)
+    assert (M, N) == (M2, N2)
+    gz = torch.empty(gy.shape, dtype=_F32, device=gy.device)
+    L = lib()
+    L.check(L.vcr_act_bwd(gy.data_ptr(), ldg, y.data_ptr(), ldy, M, N, float(slope), gz.data_ptr(), N, _stream(gy)),
+            "vcr_act_bwd")
+    return gz
+
+
+def gather_max_bwd(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float, gout: torch.Tensor,
+                   gp: torch.Tensor, gq: torch.Tensor):
+    """backward of gather_max: gq written, gp (pre-zeroed) accumulated; all [B,N,C] row views."""
+    B, N, C = p.shape
+    _, _, ldp = _rows(p); _, _, ldq = _rows(q); _, _, ldo = _rows(gout)
+    _, _, ldgp = _rows(gp); _, _, ldgq = _rows(gq)
+    L = lib()
+    L.check(L.vcr_gather_max_bwd(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), idx.shape[2], N, B * N, C,
+                                 float(slope), gout.data_ptr(), ldo, gp.data_ptr(), ldgp, gq.data_ptr(), ldgq,
+                                 _stream(p)), "vcr_gather_max_bwd")
+
+
+def edge_gather_act(pq: torch.Tensor, idx: torch.Tensor, slope: float):
+    """pq [B,N,2C] = [P|Q], idx int32 [B,N,k] -> e1 [B*N*k, C] = act(P[nbr] + Q[centre])."""
+    _chk(pq, "pq")
+    B, N, C2 = pq.shape
+    C = C2 // 2
+    k = idx.shape[2]
+    _, _, ldpq = _rows(pq)
+    E = torch.empty((B * N * k, C), dtype=_F32, device=pq.device)
+    L = lib()
+    L.check(L.vcr_edge_gather_act(pq.data_ptr(), ldpq, idx.data_ptr(), k, N, B * N, C, float(slope), E.data_ptr(),
+                                  _stream(pq)), "vcr_edge_gather_act")
+    return E
+
+
+def edge_max_bwd_(z: torch.Tensor, gx: torch.Tensor, k: int, slope: float):
+    """z [T*k, C] (convDG2 pre-activations) -> in place g_z; gx [T, C] row view."""
+    _chk(z, "z"); _chk(gx, "gx")
+    T, C, ldg = _rows(gx)
+    assert z.is_contiguous() and z.shape == (T * k, C)
+    L = lib()
+    L.check(L.vcr_edge_max_bwd(z.data_ptr(), gx.data_ptr(), ldg, k, T, C, float(slope), _stream(z)), "vcr_edge_max_bwd")
+    return z
+
+
+def edge_bwd_scatter(e: torch.Tensor, ge: torch.Tensor, gx1: torch.Tensor, idx: torch.Tensor, slope: float):
+    """e, ge [T*k, C]; gx1 [T, C] row view; idx int32 [B,N,k] -> gPQ [B,N,2C] = [gP | gQ]."""
+    B, N, k = idx.shape
+    T, C, ldg = _rows(gx1)
+    assert T == B * N and e.is_contiguous() and ge.is_contiguous()
+    gpq = torch.zeros((B, N, 2 * C), dtype=_F32, device=e.device)
+    L = lib()
+    L.check(L.vcr_edge_bwd_scatter(e.data_ptr(), ge.data_ptr(), gx1.data_ptr(), ldg, idx.data_ptr(), k, N, T, C,
+                                   float(slope), gpq.data_ptr(), 2 * C, _stream(e)), "vcr_edge_bwd_scatter")
+    return gpq
 
 
 # --------------------------------------------------------------------------------------------------

@@ -36,3 +36,28 @@ def gather_results(local: torch.Tensor, n_items: int, dst: int = 0):
     if r != dst:
         return None
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def allreduce_gradients(module: torch.nn.Module, average: bool = True):
+    """Data-parallel LPD pre-training (BASELINE config 3 at N > 1): ONE all-reduce of the flattened fp32 gradient
+    (5.6 M parameters for the full VCRNet, 0.4 M for the LPDNet embedding) per step -- the only collective in the
+    framework (NCCL over NVLink on GPUs; gloo in the CPU tests).  Replaces nn.DataParallel's per-step replicate +
+    reduce in the reference's train loop (util/initPara.py:260, model/lpdnet_model.py:232-276).
+    Parameters without a gradient contribute zeros so every rank reduces the same layout."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= dist.get_world_size()
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return off
