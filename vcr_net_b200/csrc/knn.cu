@@ -248,6 +248,7 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
 
             const float* qrow = Qs + (qg * 8) * DCP;
             const float* crow = Cs + (cg * 256 + lane) * DCP;
+            if (j0 + cg * 256 >= N) continue;      // this warp's 256 candidates are all past N (e.g. N = 768): warp-uniform
 #pragma unroll 1   // (a fully unrolled body makes ptxas rotate the 64 accumulators: +20% MOVs and spills at 128 regs)
             for (int d4 = 0; d4 < DCH / 4; ++d4) {
 #pragma unroll

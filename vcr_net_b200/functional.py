@@ -87,7 +87,14 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
     h2 = ops.gemm(h1, W["w2"], W["b2"], act=1, slope=slope)                  # :112  [B,N,64]
     if idx_feat is None:
         idx_feat = ops.knn_topk(h2, k, token_major=True)                     # :122 (feature-space kNN)
-    pq1 = ops.gemm(h2, W["dg1_w"], W["dg1_b"])                               # [B,N,256] = [P|Q]
+    tc = config.precision != "fp32"
+    if tc:     # K = 64 / 128 products are output-bandwidth bound: 3-term split on tensor cores in every TC mode
+        wpq = packed(m, "pq_h3", [m.convDG1[0].weight, m.convSN1[0].weight],
+                     lambda: (ops.to_operand(W["dg1_w"], "h3"), ops.to_operand(W["sn1_w"], "h3")))
+        pq1 = torch.empty((B, N, 256), dtype=_F32, device=xyz.device)
+        ops.gemm_tc(ops.to_operand(h2, "h3"), wpq[0], B * N, 256, 64, bias=W["dg1_b"], c=pq1)
+    else:
+        pq1 = ops.gemm(h2, W["dg1_w"], W["dg1_b"])                           # [B,N,256] = [P|Q]
     cat = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
     if config.precision == "fp32":
         ops.edgeconv_dg(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256])  # :123-126
@@ -96,7 +103,11 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
                            config.precision)
     if idx_xyz is None:
         idx_xyz = ops.knn_topk(xyz, k, token_major=False)                    # :129 (3-d kNN)
-    pq3 = ops.gemm(cat[:, :, 128:256], W["sn1_w"], W["sn1_b"])               # [B,N,512] = [P3|Q3]
+    if tc:
+        pq3 = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
+        ops.gemm_tc(ops.to_operand(cat[:, :, 128:256], "h3"), wpq[1], B * N, 512, 128, bias=W["sn1_b"], c=pq3)
+    else:
+        pq3 = ops.gemm(cat[:, :, 128:256], W["sn1_w"], W["sn1_b"])           # [B,N,512] = [P3|Q3]
     ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_xyz, slope, cat[:, :, 256:512])  # :130-132
     mode = config.precision
     if mode == "fp32":
