@@ -178,6 +178,12 @@ int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, 
                   long long stride_in, long long stride_out, cudaStream_t stream);
 int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 
+/* ---- DGCNN / PointNet embeddings (--emb_nn dgcnn | pointnet, model/vcrnet_model.py:66-123) ----------
+ * The per-edge 1x1 conv stack runs as GEMMs over a materialised [T*k, C] edge tensor (vcr_edge_gather_act builds
+ * layer 1 from the split first conv, vcr_gemm_* the rest with eval-mode BatchNorm folded into weight and bias);
+ * vcr_edge_max is x.max(dim=-1): out[pt, c] = max_kk E[pt, kk, c]. */
+int vcr_edge_max(const float* E, int k, long long total_pts, int C, float* out, int ldo, cudaStream_t stream);
+
 /* ---- LPDNet backward (BASELINE config 3: LPD pre-training forward + backward) ------------------------
  * The reference differentiates model/lpdnet_model.py:103-137 with autograd (loss at :149-229, optimiser step in
  * train_one_epoch :232-276).  These are the gradient kernels of the factored forward (csrc/train.cu); the dense

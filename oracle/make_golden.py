@@ -174,6 +174,7 @@ def main():
              src_emb=N_(se_l))
 
     make_lpd_train(ref, lpd_sd)
+    make_variants(ref)
 
 
 def make_lpd_train(ref=None, lpd_sd=None):
@@ -218,8 +219,57 @@ def make_lpd_train(ref=None, lpd_sd=None):
          Rw_keep_bits=np.packbits(N_(keep).reshape(-1)), loss=N_(loss), mse=N_(mse), mae=N_(mae), **ga, **gb)
 
 
+def make_variants(ref=None):
+    """the flag-selectable embeddings (--emb_nn dgcnn | pointnet) and heads
+    (--vcp_nn att | dist), eval mode, from the live reference.  BatchNorm running statistics and affine parameters are
+    randomised so that folding them into the convs is actually exercised."""
+    torch.set_num_threads(1)
+    if ref is None:
+        ref = ref_harness.import_reference()
+    VM, U = ref.vcrnet_model, ref.util
+    torch.manual_seed(11)
+    rng = np.random.RandomState(11)
+    out = {}
+
+    def randomise_bn(net):
+        for mod in net.modules():
+            if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                n = mod.num_features
+                mod.running_mean.copy_(T(rng.normal(0, 0.2, n).astype(np.float32)))
+                mod.running_var.copy_(T(rng.uniform(0.5, 1.5, n).astype(np.float32)))
+                mod.weight.data.copy_(T(rng.uniform(0.5, 1.5, n).astype(np.float32)))
+                mod.bias.data.copy_(T(rng.normal(0, 0.1, n).astype(np.float32)))
+
+    pa = synth.make_pairs(2, 256, first_item=90)
+    x = pa["src"]
+    with torch.no_grad():
+        for name, cls in (("dgcnn", VM.DGCNN), ("pointnet", VM.PointNet)):
+            net = cls(emb_dims=128).eval()
+            randomise_bn(net)
+            for k, v in net.state_dict().items():
+                if "num_batches_tracked" not in k:
+                    out[f"{name}.{k}"] = N_(v)
+            out[f"{name}.out"] = N_(net(T(x)))
+        out["x"] = x
+        out["idx"] = N_(U.knn(T(x), 20)).astype(np.int32)
+        # heads on 64-d embeddings of 128 points
+        se = rng.standard_normal((2, 64, 128)).astype(np.float32)
+        te = rng.standard_normal((2, 64, 128)).astype(np.float32)
+        ph = synth.make_pairs(2, 128, first_item=95)
+        args = ref_harness.default_args(emb_dims=64)
+        att = VM.VcpAtt(args).eval()
+        for k, v in att.state_dict().items():
+            out[f"att.{k}"] = N_(v)
+        out.update(h_src_emb=se, h_tgt_emb=te, h_src=ph["src"], h_tgt=ph["tgt"],
+                   att_corr=N_(att(T(se), T(te), T(ph["src"]), T(ph["tgt"]))[1]),
+                   dist_corr=N_(VM.VcpByDis(args)(T(se), T(te), T(ph["src"]), T(ph["tgt"]))[1]))
+    save("variants", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        make_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
         make_lpd_train()
     else:
         main()

@@ -56,7 +56,8 @@ def conv1x1(x, w, b):
     w2 = w.reshape(w.shape[0], w.shape[1])
     lead = x.shape[2:]
     y = np.matmul(w2, x.reshape(x.shape[0], x.shape[1], -1))
-    y = y + b.reshape(1, -1, 1)
+    if b is not None:
+        y = y + b.reshape(1, -1, 1)
     return y.reshape((x.shape[0], w2.shape[0]) + lead).astype(F32)
 
 
@@ -177,6 +178,35 @@ def lpdnet_forward(p, x, slope=0.0, prefix="emb_nn.", k=20, idx_feat=None, idx_x
     return out
 
 
+def batch_norm_eval(x, p, prefix, eps=1e-5):
+    """nn.BatchNorm1d/2d in eval mode: channel axis 1, running statistics."""
+    sh = (1, -1) + (1,) * (x.ndim - 2)
+    mean, var = p[prefix + ".running_mean"].reshape(sh), p[prefix + ".running_var"].reshape(sh)
+    w, b = p[prefix + ".weight"].reshape(sh), p[prefix + ".bias"].reshape(sh)
+    return _f32((x - mean) / np.sqrt(var + np.float32(eps)) * w + b)
+
+
+def dgcnn_forward(p, x, prefix="", k=20, idx=None):
+    """DGCNN.forward (model/vcrnet_model.py:105-123), eval mode.  x [B,3,N] -> [B,emb_dims,N]."""
+    x = _f32(x)
+    g = lambda name: p[prefix + name]
+    e = get_graph_feature(x, k, idx)                                                    # :107 [B,6,N,k]
+    outs = []
+    for i in (1, 2, 3, 4):                                                              # :109-119
+        e = np.maximum(batch_norm_eval(conv1x1(e, g(f"conv{i}.weight"), None), p, prefix + f"bn{i}"), 0)
+        outs.append(e.max(axis=-1))
+    cat = np.concatenate(outs, axis=1)                                                  # :120
+    return np.maximum(batch_norm_eval(conv1x1(cat, g("conv5.weight"), None), p, prefix + "bn5"), 0)   # :122
+
+
+def pointnet_forward(p, x, prefix=""):
+    """PointNet.forward (model/vcrnet_model.py:82-88), eval mode."""
+    h = _f32(x)
+    for i in range(1, 6):
+        h = np.maximum(batch_norm_eval(conv1x1(h, p[prefix + f"conv{i}.weight"], None), p, prefix + f"bn{i}"), 0)
+    return h
+
+
 # --------------------------------------------------------------------------------------
 # Transformer pointer (model/transformer.py)
 # --------------------------------------------------------------------------------------
@@ -285,6 +315,21 @@ def get_copair_all(src, src_emb, tgt, tgt_emb):
     scores = softmax(neg_sqdist_cross(src_emb, tgt_emb), 2)
     src_corr = np.matmul(_f32(tgt), scores.transpose(0, 2, 1))
     return _f32(src), src_corr.astype(F32)
+
+
+def vcp_by_dis(src_emb, tgt_emb, src, tgt):
+    """VcpByDis.forward (model/vcrnet_model.py:407-421)."""
+    d_k = src_emb.shape[1]
+    scores = _f32(np.matmul(src_emb.transpose(0, 2, 1), tgt_emb) / np.float32(math.sqrt(d_k)))
+    scores = softmax(scores, axis=2)
+    return src, _f32(np.matmul(tgt, scores.transpose(0, 2, 1)))
+
+
+def vcp_att(p, prefix, src_emb, tgt_emb, src, tgt):
+    """VcpAtt.forward (model/vcrnet_model.py:434-460): Linear on both embeddings, then the getCopairALL arithmetic."""
+    q = linear(src_emb.transpose(0, 2, 1), p[prefix + "linears_emb.0.weight"], p[prefix + "linears_emb.0.bias"])
+    k = linear(tgt_emb.transpose(0, 2, 1), p[prefix + "linears_emb.1.weight"], p[prefix + "linears_emb.1.bias"])
+    return get_copair_all(src, np.ascontiguousarray(q.transpose(0, 2, 1)), tgt, np.ascontiguousarray(k.transpose(0, 2, 1)))
 
 
 def _gather_cols(x, idx):

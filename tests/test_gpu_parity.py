@@ -506,3 +506,50 @@ def test_flash_attention_shapes_and_rescale(Nq, Nk, spread):
     sc = (q.astype(np.float64) @ k.astype(np.float64).transpose(0, 1, 3, 2)) / np.sqrt(dk)
     ref_lse = (np.log(np.exp(sc - sc.max(-1, keepdims=True)).sum(-1)) + sc.max(-1)) / np.log(2.0)
     assert np.abs(nump(lse) - ref_lse).max() < 1e-3 * max(1.0, np.abs(ref_lse).max())
+
+
+# ---------------------------------------------------------------- embeddings / heads variants ----------
+def _load_prefixed(module, g, prefix):
+    sd = {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items()
+          if k.startswith(prefix) and not k.endswith(".out")}
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.endswith("num_batches_tracked") for m in missing), (missing, unexpected)
+
+
+def test_dgcnn_pointnet_vs_golden(precision):
+    g = load_golden("variants")
+    x = cu(g["x"])
+    net = V.DGCNN(emb_dims=128).to(DEV).eval()
+    _load_prefixed(net, g, "dgcnn.")
+    out = net(x, idx=cu(g["idx"], torch.int32))
+    assert tuple(out.shape) == (2, 128, 256)
+    assert rel_err(nump(out), g["dgcnn.out"]) < TOL
+    assert rel_err(nump(net(x)), g["dgcnn.out"]) < 5e-4            # free-running kNN (near-tie flips, cf. LPDNet)
+    pn = V.PointNet(emb_dims=128).to(DEV).eval()
+    _load_prefixed(pn, g, "pointnet.")
+    assert rel_err(nump(pn(x)), g["pointnet.out"]) < TOL
+    with pytest.raises(RuntimeError):
+        net.train()(x)                                             # batch-statistics BatchNorm is not implemented
+
+
+def test_vcp_att_dist_heads_vs_golden(precision):
+    g = load_golden("variants")
+    args = default_args(emb_dims=64, vcp_nn="att")
+    att = V.VcpAtt(args).to(DEV).eval()
+    att.load_state_dict({k[len("att."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("att.")}, strict=True)
+    se, te, s, t = cu(g["h_src_emb"]), cu(g["h_tgt_emb"]), cu(g["h_src"]), cu(g["h_tgt"])
+    s_out, c = att(se, te, s, t)
+    assert torch.equal(s_out, s) and rel_err(nump(c), g["att_corr"]) < TOL
+    _, c = V.VcpByDis(args)(se, te, s, t)
+    assert rel_err(nump(c), g["dist_corr"]) < TOL
+
+
+def test_vcrnet_with_dgcnn_and_att_head_runs(ckpt):
+    """--emb_nn dgcnn --vcp_nn att assembles and registers a pair (random init; checks wiring + a proper rotation)."""
+    torch.manual_seed(3)
+    net = V.VCRNet(default_args(emb_nn="dgcnn", vcp_nn="att")).to(DEV).eval()
+    p = synth.make_pairs(2, 256, first_item=9)
+    out = V.vcrnetIter(net, cu(p["src"]), cu(p["tgt"]), iter=2)
+    R = nump(out[2])
+    assert np.allclose(np.matmul(R, R.transpose(0, 2, 1)), np.eye(3)[None], atol=1e-5)
+    assert np.allclose(np.linalg.det(R), 1.0, atol=1e-5)

@@ -114,6 +114,22 @@ edgeconv_dg_kernel(const float* __restrict__ PQ, int ldpq, const int* __restrict
     }
 }
 
+__global__ void edge_max_kernel(const float* __restrict__ E, int k, long long total_pts, int C, float* __restrict__ out,
+                                int ldo) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C4 = C >> 2;
+    if (e >= total_pts * C4) return;
+    const long long pt = e / C4;
+    const int c4 = (int)(e - pt * C4);
+    const float4* r = reinterpret_cast<const float4*>(E + pt * k * C) + c4;
+    float4 m = r[0];
+    for (int kk = 1; kk < k; ++kk) {
+        const float4 t = r[(size_t)kk * C4];
+        m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
+    }
+    *reinterpret_cast<float4*>(out + pt * ldo + c4 * 4) = m;
+}
+
 // out[pt, c] = act( max_k P[cloud0 + idx[pt,k], c] + Q[pt, c] ),  C % 128 == 0: one warp per point
 template <int VPL>
 __global__ void gather_max_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ Q, int ldq,
@@ -199,6 +215,15 @@ VCR_API int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, con
         case 3: gather_max_kernel<3><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
         case 4: gather_max_kernel<4><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
     }
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// out[pt, c] = max_kk E[pt, kk, c]   (x.max(dim=-1) over a materialised per-edge tensor, DGCNN model/vcrnet_model.py:108-118)
+VCR_API int vcr_edge_max(const float* E, int k, long long total_pts, int C, float* out, int ldo, cudaStream_t stream) {
+    VCR_REQUIRE(E && out && k >= 1 && total_pts > 0 && C > 0 && C % 4 == 0 && ldo % 4 == 0);
+    const long long n = total_pts * (C / 4);
+    edge_max_kernel<<<vcr_cdiv(n, 256), 256, 0, stream>>>(E, k, total_pts, C, out, ldo);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }

@@ -15,7 +15,8 @@ import runpy
 import sys
 
 HOT_PATH = {
-    "model.vcrnet_model": ["VCRNet", "VcpTopK", "SVDHead", "Identity", "vcrnetIter"],
+    "model.vcrnet_model": ["VCRNet", "VcpTopK", "VcpAtt", "VcpByDis", "SVDHead", "Identity", "vcrnetIter", "DGCNN",
+                           "PointNet"],
     "model.lpdnet_model": ["LPDNet", "LPD"],
     "model.transformer": ["Transformer", "MultiHeadedAttention", "PositionwiseFeedForward", "LayerNorm",
                           "EncoderDecoder", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer",

@@ -208,6 +208,95 @@ def lpdnet_tokens_train(m, xyz, idx_feat=None, idx_xyz=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# DGCNN / PointNet embeddings (--emb_nn dgcnn | pointnet; model/vcrnet_model.py:66-123)
+# --------------------------------------------------------------------------------------------------
+
+def _fold_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the bias-free 1x1 conv in front of it: y = (W x - mean) * g / sqrt(var + eps) + b."""
+    w = conv.weight.detach().reshape(conv.weight.shape[0], -1)
+    s = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    return (w * s[:, None]).contiguous(), (bn.bias.detach() - bn.running_mean.detach() * s).contiguous()
+
+
+def _bn_params(m, n):
+    ps = []
+    for i in range(1, n + 1):
+        bn = getattr(m, f"bn{i}")
+        ps += [getattr(m, f"conv{i}").weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    return ps
+
+
+def _require_eval(m):
+    if m.training:
+        raise RuntimeError(f"{type(m).__name__}: only eval() mode (running BatchNorm statistics folded into the convs) is "
+                           "implemented on the B200 path; call .eval() as the reference's test loop does")
+
+
+def _edge_mlp(e_prev, w, b, mode, want_operand):
+    """One per-edge 1x1 conv + folded BN + ReLU over a materialised [T*k, Cin] edge tensor."""
+    if mode == "fp32":
+        return ops.gemm(e_prev, w, b, act=1, slope=0.0), None
+    rows = e_prev.rows if isinstance(e_prev, ops.Operand) else e_prev.shape[0]
+    a = e_prev if isinstance(e_prev, ops.Operand) else ops.to_operand(e_prev, mode)
+    co, ci = w.shape
+    out = torch.empty((rows, co), dtype=_F32, device=w.device)
+    h = ops.Operand.empty(rows, co, mode, w.device) if want_operand else None
+    ops.gemm_tc(a, ops.to_operand(w, mode), rows, co, ci, bias=b, act=1, slope=0.0, c=out,
+                **({"h": h, "h_split": co} if want_operand else {}))
+    return out, h
+
+
+def dgcnn_tokens(m, xyz: torch.Tensor, idx=None, stages=None):
+    """DGCNN.forward (model/vcrnet_model.py:105-123): xyz [B,3,N] -> tokens [B,N,emb_dims].
+    conv1 acts on the raw concat [x_j ; x_i] (util/util.py:197) so it splits into per-point products P + Q like the
+    LPDNet EdgeConvs; conv2..4 are per-edge GEMMs over [T*k, C]; every max over k is vcr_edge_max."""
+    _require_eval(m)
+    mode = config.precision
+    k = 20
+    B, _, N = xyz.shape
+    xyz = xyz.contiguous()
+
+    def build():
+        w1, b1 = _fold_bn(m.conv1, m.bn1)                                   # [64,6]
+        stacked = torch.cat([w1[:, :3], w1[:, 3:]], dim=0).contiguous()     # [P | Q] rows
+        bias = torch.cat([torch.zeros_like(b1), b1]).contiguous()
+        return {"w1": stacked, "b1": bias, **{f"w{i}": _fold_bn(getattr(m, f"conv{i}"), getattr(m, f"bn{i}"))
+                                              for i in (2, 3, 4, 5)}}
+
+    W = packed(m, "dgcnn", _bn_params(m, 5), build)
+    if idx is None:
+        idx = ops.knn_topk(xyz, k, token_major=False)                       # get_graph_feature(x) -> knn(x, 20)
+    pq1 = ops.conv3_act(xyz, W["w1"], W["b1"], 1.0)                          # slope 1 = identity: [B,N,128] = [P|Q]
+    cat = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
+    e = ops.edge_gather_act(pq1, idx, 0.0)                                   # relu(bn1(conv1(edge)))  [T*k,64]
+    ops.edge_max(e, k, cat[:, :, 0:64])                                      # x1
+    e, eop = _edge_mlp(e, *W["w2"], mode, True)
+    ops.edge_max(e, k, cat[:, :, 64:128])                                    # x2
+    e, eop = _edge_mlp(eop if eop is not None else e, *W["w3"], mode, True)
+    ops.edge_max(e, k, cat[:, :, 128:256])                                   # x3
+    e, _ = _edge_mlp(eop if eop is not None else e, *W["w4"], mode, False)
+    ops.edge_max(e, k, cat[:, :, 256:512])                                   # x4
+    emb, _ = _edge_mlp(cat.view(B * N, 512), *W["w5"], mode, False)          # relu(bn5(conv5(cat)))
+    if stages is not None:
+        stages.update(idx=idx, cat=cat)
+    return emb.view(B, N, -1)
+
+
+def pointnet_tokens(m, xyz: torch.Tensor):
+    """PointNet.forward (model/vcrnet_model.py:82-88): five per-point conv + BN + ReLU layers."""
+    _require_eval(m)
+    mode = config.precision
+    B, _, N = xyz.shape
+    W = packed(m, "pointnet", _bn_params(m, 5),
+               lambda: {f"w{i}": _fold_bn(getattr(m, f"conv{i}"), getattr(m, f"bn{i}")) for i in range(1, 6)})
+    h = ops.conv3_act(xyz.contiguous(), W["w1"][0], W["w1"][1], 0.0).view(B * N, -1)
+    hop = None
+    for i in (2, 3, 4, 5):
+        h, hop = _edge_mlp(hop if hop is not None else h, *W[f"w{i}"], mode, i < 5)
+    return h.view(B, N, -1)
+
+
+# --------------------------------------------------------------------------------------------------
 # Transformer
 # --------------------------------------------------------------------------------------------------
 
@@ -420,18 +509,21 @@ def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_inp
 # VCP head
 # --------------------------------------------------------------------------------------------------
 
-def pair_dots(src_tok, tgt_tok):
-    """dot[b,i,j] = s_i . t_j (the matmul of model/vcrnet_model.py:337): fp32 SIMT or 3-term tensor cores.
+def pair_dots(src_tok, tgt_tok, alpha=1.0):
+    """dot[b,i,j] = alpha * s_i . t_j (the matmul of model/vcrnet_model.py:337): fp32 SIMT or 3-term tensor cores.
     The throughput modes keep the 3-term split here: these logits cancel catastrophically
     (|f|^2 ~ 500 against gaps < 1), SURVEY.md section 7 hard part 2."""
     if config.precision == "fp32":
-        return ops.pair_dots(src_tok, tgt_tok)
+        dot, ld = ops.pair_dots(src_tok, tgt_tok)
+        if alpha != 1.0:
+            dot.mul_(alpha)
+        return dot, ld
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
     ld = (Nt + 3) // 4 * 4
     dot = torch.empty((B, Ns, ld), dtype=_F32, device=src_tok.device)
     ops.gemm_tc(ops.to_operand(src_tok, "h3"), ops.to_operand(tgt_tok, "h3"), Ns, Nt, D, nbo=B,
-                a_off=(Ns, 0, 0, 0), b_off=(Nt, 0, 0, 0), c=dot, c_strides=(Ns * ld, 0))
+                a_off=(Ns, 0, 0, 0), b_off=(Nt, 0, 0, 0), alpha=alpha, c=dot, c_strides=(Ns * ld, 0))
     return dot, ld
 
 
@@ -443,6 +535,26 @@ def vcp_whole(src_tok, tgt_tok, tgt_xyz):
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
     corr, _, _ = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=tgt_xyz.contiguous(), mode=0)
     return corr
+
+
+def vcp_by_dis(src_tok, tgt_tok, tgt_xyz):
+    """VcpByDis.forward (model/vcrnet_model.py:402-421): softmax_j(s_i . t_j / sqrt(d_k)), src_corr = tgt P^T.
+    Runs through the same fused row pass as getCopairALL with logits 2*(dot/(2 sqrt d_k)) - 0 - 0."""
+    B, Ns, D = src_tok.shape
+    Nt = tgt_tok.shape[1]
+    dot, ld = pair_dots(src_tok, tgt_tok, alpha=0.5 / math.sqrt(D))
+    zs = torch.zeros((B, Ns), dtype=_F32, device=src_tok.device)
+    zt = torch.zeros((B, Nt), dtype=_F32, device=src_tok.device)
+    corr, _, _ = ops.softcorr_rows(dot, ld, Ns, Nt, zs, zt, tgt=tgt_xyz.contiguous(), mode=0)
+    return corr
+
+
+def vcp_att(m, src_tok, tgt_tok, tgt_xyz):
+    """VcpAtt.forward (model/vcrnet_model.py:424-460): two Linear(emb, emb) projections, then the getCopairALL arithmetic
+    (linears_3d exist in the state_dict but are unused by the reference forward)."""
+    q = ops.gemm(src_tok.contiguous(), m.linears_emb[0].weight, m.linears_emb[0].bias)
+    k = ops.gemm(tgt_tok.contiguous(), m.linears_emb[1].weight, m.linears_emb[1].bias)
+    return vcp_whole(q, k, tgt_xyz)
 
 
 def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):

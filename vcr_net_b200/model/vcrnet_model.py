@@ -33,6 +33,44 @@ class Identity(nn.Module):
         return input
 
 
+class PointNet(nn.Module):
+    """model/vcrnet_model.py:66-88 (--emb_nn pointnet).  Same parameter / buffer names as the reference
+    (conv1..5 bias-free Conv1d, bn1..5 BatchNorm1d); eval-mode forward on the CUDA path."""
+
+    def __init__(self, emb_dims=512):
+        super().__init__()
+        dims = [3, 64, 64, 64, 128, emb_dims]
+        for i in range(5):
+            setattr(self, f"conv{i + 1}", nn.Conv1d(dims[i], dims[i + 1], kernel_size=1, bias=False))
+        for i in range(5):
+            setattr(self, f"bn{i + 1}", nn.BatchNorm1d(dims[i + 1]))
+
+    def forward_tokens(self, x):
+        return Fn.pointnet_tokens(self, x)
+
+    def forward(self, x):
+        return ops.transpose_batched(self.forward_tokens(x))
+
+
+class DGCNN(nn.Module):
+    """model/vcrnet_model.py:90-123 (--emb_nn dgcnn).  Same parameter / buffer names as the reference
+    (conv1..5 bias-free Conv2d, bn1..5 BatchNorm2d); eval-mode forward on the CUDA path."""
+
+    def __init__(self, emb_dims=512):
+        super().__init__()
+        dims = [(6, 64), (64, 64), (64, 128), (128, 256), (512, emb_dims)]
+        for i, (ci, co) in enumerate(dims):
+            setattr(self, f"conv{i + 1}", nn.Conv2d(ci, co, kernel_size=1, bias=False))
+        for i, (ci, co) in enumerate(dims):
+            setattr(self, f"bn{i + 1}", nn.BatchNorm2d(co))
+
+    def forward_tokens(self, x, idx=None, stages=None):
+        return Fn.dgcnn_tokens(self, x, idx=idx, stages=stages)
+
+    def forward(self, x, idx=None):
+        return ops.transpose_batched(self.forward_tokens(x, idx=idx))
+
+
 class VcpTopK(nn.Module):
     """model/vcrnet_model.py:162-347.  forward(src_emb, tgt_emb [B,D,N], src, tgt [B,3,N]) -> (src, src_corr)."""
 
@@ -69,6 +107,41 @@ class VcpTopK(nn.Module):
         return s, c
 
 
+class VcpByDis(nn.Module):
+    """model/vcrnet_model.py:402-421 (--vcp_nn dist): scaled-dot softmax correspondences."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.emb_nn = args.emb_nn
+
+    def forward_tokens(self, src_tok, tgt_tok, src, tgt):
+        return src, Fn.vcp_by_dis(src_tok.contiguous(), tgt_tok.contiguous(), tgt)
+
+    def forward(self, *input):
+        return self.forward_tokens(ops.transpose_batched(input[0]), ops.transpose_batched(input[1]), input[2], input[3])
+
+
+class VcpAtt(nn.Module):
+    """model/vcrnet_model.py:424-460 (--vcp_nn att).  Same parameters as the reference: linears_emb.{0,1} (used) and
+    linears_3d.{0,1} (present in the checkpoint, unused by the reference forward)."""
+
+    def __init__(self, args):
+        super().__init__()
+        from .transformer import clones
+        self.emb_dims = args.emb_dims
+        self.linears_emb = clones(nn.Linear(self.emb_dims, self.emb_dims), 2)
+        self.linears_3d = clones(nn.Linear(3, 3), 2)
+        self.attn = None
+        self.dropout = None
+        self.mask = None
+
+    def forward_tokens(self, src_tok, tgt_tok, src, tgt):
+        return src, Fn.vcp_att(self, src_tok, tgt_tok, tgt)
+
+    def forward(self, *input):
+        return self.forward_tokens(ops.transpose_batched(input[0]), ops.transpose_batched(input[1]), input[2], input[3])
+
+
 class SVDHead(nn.Module):
     """model/vcrnet_model.py:350-399.  forward(src, src_corr [B,3,M]) -> (R [B,3,3], t [B,3])."""
 
@@ -90,20 +163,28 @@ class VCRNet(nn.Module):
         super().__init__()
         self.emb_dims = args.emb_dims
         self.cycle = args.cycle
-        if args.emb_nn == 'lpdnet':
+        if args.emb_nn == 'pointnet':                      # :468-475
+            self.emb_nn = PointNet(emb_dims=self.emb_dims)
+        elif args.emb_nn == 'dgcnn':
+            self.emb_nn = DGCNN(emb_dims=self.emb_dims)
+        elif args.emb_nn == 'lpdnet':
             self.emb_nn = LPDNet(args)
         else:
-            raise Exception('Not implemented')           # pointnet / dgcnn: SURVEY.md section 8(f)
+            raise Exception('Not implemented')
         if args.pointer == 'identity':
             self.pointer = Identity()
         elif args.pointer == 'transformer':
             self.pointer = Transformer(args=args)
         else:
             self.pointer = None
-        if args.vcp_nn == 'topK':
+        if args.vcp_nn == 'topK':                          # :484-491
             self.head = VcpTopK(args=args)
+        elif args.vcp_nn == 'att':
+            self.head = VcpAtt(args=args)
+        elif args.vcp_nn == 'dist':
+            self.head = VcpByDis(args=args)
         else:
-            raise Exception("Not implemented")            # att / dist heads: SURVEY.md section 8(f)
+            raise Exception("Not implemented")
         self.svd = SVDHead(args=args)
 
     @torch.no_grad()      # registration INFERENCE path: only the LPD pre-training path (LPD / LPDNet) has a backward

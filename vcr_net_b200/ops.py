@@ -311,6 +311,16 @@ def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float
                              float(slope), out.data_ptr(), ldo, _stream(p)), "vcr_gather_max")
 
 
+def edge_max(e: torch.Tensor, k: int, out: torch.Tensor):
+    """e [T*k, C] contiguous -> out [T, C] row view: max over the k edges of each point."""
+    _chk(e, "e")
+    T, C, ldo = _rows(out)
+    assert e.is_contiguous() and e.shape == (T * k, C)
+    L = lib()
+    L.check(L.vcr_edge_max(e.data_ptr(), k, T, C, out.data_ptr(), ldo, _stream(e)), "vcr_edge_max")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # LPDNet backward pieces (csrc/train.cu)
 # --------------------------------------------------------------------------------------------------
