@@ -178,6 +178,19 @@ int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, 
                   long long stride_in, long long stride_out, cudaStream_t stream);
 int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 
+/* ---- ICP refinement (--iter=0): model/icp_model.py:26-108 ICP.forward, model/vcrnet_model.py:46-62 -----------
+ * vcr_icp_nearest = nearest_neighbor (:52-75): corr [B,3,Ns] = nearest dst point per src point under
+ * pd = (-xx - (-2 s.d)) - yy (ties -> lower index); *err_sum (double, caller-zeroed) += sum of the best pd.
+ * vcr_icp_advance = loop tail (:36-40) with the convergence test on the device: if the state's done flag is clear,
+ * src <- R src + t, mean = *err_sum / (B*Ns), done = |prev - mean| < tolerance, prev = mean.  state is
+ * vcr_icp_state_bytes() bytes {int done; int iters; double prev_error}, zeroed before the first iteration.
+ * The rigid fit between the two calls is vcr_svd_head (best_fit_transform :77-108 == SVDHead arithmetic). */
+size_t vcr_icp_state_bytes(void);
+int vcr_icp_nearest(const float* src, const float* dst, int B, int Ns, int Nt, float* corr, int* nn_idx,
+                    double* err_sum, cudaStream_t stream);
+int vcr_icp_advance(float* src, const float* R, const float* t, int B, int Ns, const double* err_sum,
+                    float tolerance, void* state, cudaStream_t stream);
+
 /* ---- DGCNN / PointNet embeddings (--emb_nn dgcnn | pointnet, model/vcrnet_model.py:66-123) ----------
  * The per-edge 1x1 conv stack runs as GEMMs over a materialised [T*k, C] edge tensor (vcr_edge_gather_act builds
  * layer 1 from the split first conv, vcr_gemm_* the rest with eval-mode BatchNorm folded into weight and bias);

@@ -263,6 +263,21 @@ def make_variants(ref=None):
         out.update(h_src_emb=se, h_tgt_emb=te, h_src=ph["src"], h_tgt=ph["tgt"],
                    att_corr=N_(att(T(se), T(te), T(ph["src"]), T(ph["tgt"]))[1]),
                    dist_corr=N_(VM.VcpByDis(args)(T(se), T(te), T(ph["src"]), T(ph["tgt"]))[1]))
+    # ICP (model/icp_model.py) on a mildly perturbed copy: converges in a few iterations, exercising the early break
+    IM = ref.icp_model if hasattr(ref, "icp_model") else __import__("model.icp_model", fromlist=["ICP"])
+    pi = synth.make_pairs(3, 256, first_item=120)
+    from scipy.spatial.transform import Rotation
+    Rs = Rotation.from_euler("zyx", [[0.08, -0.05, 0.06], [0.02, 0.1, -0.07], [0.0, 0.0, 0.0]]).as_matrix().astype(np.float32)
+    ts = np.array([[0.03, -0.02, 0.01], [-0.04, 0.0, 0.02], [0.0, 0.0, 0.0]], dtype=np.float32)
+    icp_src = pi["src"]
+    perm = np.random.RandomState(5).permutation(256)
+    icp_dst = (np.matmul(Rs, icp_src) + ts[:, :, None])[:, :, perm].astype(np.float32)
+    with torch.no_grad():
+        for mi in (10, 2):
+            o = IM.ICP(max_iterations=mi)(T(icp_src), T(icp_dst))
+            out.update({f"icp{mi}_src": N_(o[1]), f"icp{mi}_R": N_(o[2]), f"icp{mi}_t": N_(o[3]),
+                        f"icp{mi}_R_ba": N_(o[4]), f"icp{mi}_t_ba": N_(o[5])})
+    out.update(icp_in_src=icp_src, icp_in_dst=icp_dst)
     save("variants", **out)
 
 

@@ -60,8 +60,9 @@ def import_reference():
     import model.transformer as transformer
     import model.vcrnet_model as vcrnet_model
     import util.util as util
+    import model.icp_model as icp_model
     return types.SimpleNamespace(lpdnet_model=lpdnet_model, transformer=transformer,
-                                 vcrnet_model=vcrnet_model, util=util)
+                                 vcrnet_model=vcrnet_model, util=util, icp_model=icp_model)
 
 
 def default_args(partial=False, overlap2=0.75, **kw):

@@ -426,6 +426,29 @@ def vcrnet_forward(p, src, tgt, partial=False, overlap2=0.75, h=4, pointer="tran
     return (out, stages) if return_stages else out
 
 
+def icp_forward(src_init, dst, max_iterations=10, tolerance=0.001):
+    """ICP.forward (model/icp_model.py:26-50) -> (srcInit, src, R_ab, t_ab, R_ba, t_ba, iterations)."""
+    src_init, dst = _f32(src_init), _f32(dst)
+    src = src_init
+    prev = 0.0
+    iters = 0
+    for _ in range(max_iterations):
+        pd = neg_sqdist_cross(src, dst)                                     # nearest_neighbor :57-62
+        idx = pd.argmax(axis=2)
+        mean_error = float(pd.max(axis=2).mean())
+        corr = _gather_cols(dst, idx)
+        R, t = svd_head(src, corr)                                          # best_fit_transform :77-108
+        src = transform_point_cloud(src, R, t)
+        iters += 1
+        if abs(prev - mean_error) < tolerance:
+            break
+        prev = mean_error
+    R, t = svd_head(src_init, src)
+    R_ba = np.ascontiguousarray(R.transpose(0, 2, 1))
+    t_ba = (-np.matmul(R_ba, t[:, :, None])[:, :, 0]).astype(F32)
+    return src_init, src, R, t, R_ba, t_ba, iters
+
+
 def vcrnet_iter(p, src, tgt, n_iter=1, **kw):
     """model/vcrnet_model.py:21-43: R_f <- R_i R_f, t_f <- R_i t_f + t_i, inverse at the end."""
     cur = _f32(src)

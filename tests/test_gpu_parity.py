@@ -553,3 +553,53 @@ def test_vcrnet_with_dgcnn_and_att_head_runs(ckpt):
     R = nump(out[2])
     assert np.allclose(np.matmul(R, R.transpose(0, 2, 1)), np.eye(3)[None], atol=1e-5)
     assert np.allclose(np.linalg.det(R), 1.0, atol=1e-5)
+
+
+def test_icp_vs_golden_device_side_convergence():
+    """ICP (model/icp_model.py) with the convergence test on the device: same result as the reference's early break."""
+    g = load_golden("variants")
+    src, dst = cu(g["icp_in_src"]), cu(g["icp_in_dst"])
+    for mi, want_iters in ((10, 3), (2, 2)):
+        icp = V.ICP(max_iterations=mi).to(DEV)
+        s0, s1, R, t, R_ba, t_ba = icp(src, dst)
+        assert icp.iterations_run() == want_iters
+        assert torch.equal(s0, src)
+        for got, key in zip((s1, R, t, R_ba, t_ba), ("src", "R", "t", "R_ba", "t_ba")):
+            assert np.abs(nump(got) - g[f"icp{mi}_{key}"]).max() < 5e-6, (mi, key)
+    # nearest-neighbour kernel vs the oracle's arg-max (ties -> lower index), ragged sizes
+    rng = np.random.RandomState(3)
+    a = rng.rand(2, 3, 301).astype(np.float32) - 0.5
+    b = rng.rand(2, 3, 1111).astype(np.float32) - 0.5
+    err = torch.zeros(1, dtype=torch.float64, device=DEV)
+    corr, idx = ops.icp_nearest(cu(a), cu(b), err, want_idx=True)
+    pd = O.neg_sqdist_cross(a, b)
+    want = pd.argmax(axis=2)
+    same = nump(idx) == want
+    assert same.mean() > 0.995                       # fp32 near-ties between matmul orders only
+    assert abs(float(err) - float(pd.max(axis=2).astype(np.float64).sum())) < 1e-3
+    assert np.array_equal(nump(corr)[0][:, same[0]], b[0][:, want[0][same[0]]])
+
+
+def test_vcrnet_icp_net_refines_pose(net_whole):
+    """--iter=0 path (vcrnetIcpNet, model/vcrnet_model.py:46-62): composes the network pose with the ICP refinement."""
+    from types import SimpleNamespace
+    p = synth.make_pairs(2, 256, first_item=40)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    out = V.vcrnetIcpNet(SimpleNamespace(max_iterations=5), net_whole, src, tgt)
+    want = O.vcrnet_forward(synth_ckpt_cache(), p["src"], p["tgt"])
+    ts = O.transform_point_cloud(p["src"], want[2], want[3])
+    oi = O.icp_forward(ts, p["tgt"], max_iterations=5)
+    R_f = np.matmul(oi[2], want[2])
+    t_f = np.matmul(oi[2], want[3][:, :, None])[:, :, 0] + oi[3]
+    assert rel_err(nump(out[2]), R_f) < 2e-3 and rel_err(nump(out[3]), t_f) < 2e-3
+    R = nump(out[2])
+    assert np.allclose(np.matmul(R, R.transpose(0, 2, 1)), np.eye(3)[None], atol=1e-5)
+
+
+_CK = {}
+
+
+def synth_ckpt_cache():
+    if "ck" not in _CK:
+        _CK["ck"] = synth.make_checkpoint(1234, emb_weights=dict(load_golden("lpd_pretrained_weights")))
+    return _CK["ck"]

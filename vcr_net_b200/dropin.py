@@ -15,9 +15,10 @@ import runpy
 import sys
 
 HOT_PATH = {
-    "model.vcrnet_model": ["VCRNet", "VcpTopK", "VcpAtt", "VcpByDis", "SVDHead", "Identity", "vcrnetIter", "DGCNN",
+    "model.vcrnet_model": ["VCRNet", "VcpTopK", "VcpAtt", "VcpByDis", "SVDHead", "Identity", "vcrnetIter", "vcrnetIcpNet", "DGCNN",
                            "PointNet"],
     "model.lpdnet_model": ["LPDNet", "LPD"],
+    "model.icp_model": ["ICP"],
     "model.transformer": ["Transformer", "MultiHeadedAttention", "PositionwiseFeedForward", "LayerNorm",
                           "EncoderDecoder", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer",
                           "SublayerConnection", "clones"],
@@ -27,6 +28,7 @@ HOT_PATH = {
 _OURS = {
     "model.vcrnet_model": "vcr_net_b200.model.vcrnet_model",
     "model.lpdnet_model": "vcr_net_b200.model.lpdnet_model",
+    "model.icp_model": "vcr_net_b200.model.icp_model",
     "model.transformer": "vcr_net_b200.model.transformer",
     "util.util": "vcr_net_b200.util.util",
 }
@@ -40,7 +42,7 @@ def install(reference_root: str):
         sys.path.insert(0, reference_root)
     done = {}
     # util.util first: model.* does `from util.util import knn, ...` at import time
-    for ref_name in ("util.util", "model.transformer", "model.lpdnet_model", "model.vcrnet_model"):
+    for ref_name in ("util.util", "model.transformer", "model.lpdnet_model", "model.icp_model", "model.vcrnet_model"):
         ours = importlib.import_module(_OURS[ref_name])
         ref = importlib.import_module(ref_name)
         for sym in HOT_PATH[ref_name]:

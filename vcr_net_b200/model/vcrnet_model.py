@@ -28,6 +28,19 @@ def vcrnetIter(net, src, tgt, iter=1):
     return srcK, src_corrK, R_f, t_f, R_ba, t_ba
 
 
+def vcrnetIcpNet(args, net, src, tgt):
+    """model/vcrnet_model.py:46-62 (--iter=0): one network pass, then ICP refinement of the transformed source."""
+    from .icp_model import ICP
+    icp = ICP(max_iterations=args.max_iterations).to(src.device)
+    _, _, R, t, _, _ = net(src, tgt)
+    transformed_src = ops.rigid_apply(src, R, t)
+    _, _, R_icp, t_icp, _, _ = icp(transformed_src, tgt)
+    R_f, t_f = R.clone(), t.clone()
+    ops.pose_compose_(R_icp, t_icp, R_f, t_f)                              # R <- R_icp R, t <- R_icp t + t_icp
+    R_ba, t_ba = ops.pose_inverse(R_f, t_f)
+    return transformed_src, tgt, R_f, t_f, R_ba, t_ba
+
+
 class Identity(nn.Module):
     def forward(self, *input):
         return input

@@ -631,6 +631,36 @@ def pose_inverse(R, t):
     return Ri, ti
 
 
+def icp_nearest(src: torch.Tensor, dst: torch.Tensor, err_slot: torch.Tensor, want_idx=False):
+    """src [B,3,Ns], dst [B,3,Nt] -> corr [B,3,Ns]; err_slot (float64, 1 element, zero) accumulates sum(best pd)."""
+    _chk(src, "src"); _chk(dst, "dst")
+    src, dst = src.contiguous(), dst.contiguous()
+    B, _, Ns = src.shape
+    Nt = dst.shape[2]
+    assert err_slot.dtype == torch.float64 and err_slot.is_cuda
+    corr = torch.empty_like(src)
+    idx = torch.empty((B, Ns), dtype=torch.int32, device=src.device) if want_idx else None
+    L = lib()
+    L.check(L.vcr_icp_nearest(src.data_ptr(), dst.data_ptr(), B, Ns, Nt, corr.data_ptr(),
+                              idx.data_ptr() if want_idx else None, err_slot.data_ptr(), _stream(src)), "vcr_icp_nearest")
+    return (corr, idx) if want_idx else corr
+
+
+def icp_state(device):
+    n = lib().vcr_icp_state_bytes()
+    return torch.zeros((n + 7) // 8, dtype=torch.int64, device=device)
+
+
+def icp_advance_(src: torch.Tensor, R: torch.Tensor, t: torch.Tensor, err_slot: torch.Tensor, tolerance: float,
+                 state: torch.Tensor):
+    """In place: src <- R src + t unless the device-side state says the loop has converged; updates the state."""
+    assert src.is_contiguous()
+    B, _, Ns = src.shape
+    L = lib()
+    L.check(L.vcr_icp_advance(src.data_ptr(), R.data_ptr(), t.data_ptr(), B, Ns, err_slot.data_ptr(), float(tolerance),
+                              state.data_ptr(), _stream(src)), "vcr_icp_advance")
+
+
 def transpose_batched(x: torch.Tensor):
     """[nb,R,C] contiguous -> [nb,C,R] contiguous (module-boundary layout change)."""
     _chk(x, "x")
