@@ -137,6 +137,10 @@ int vcr_row_lse(const float* S, int ld, long long rows, int n, const uint8_t* ke
 int vcr_softmax_operand(const float* S, int ld, long long rows, int n, const uint8_t* keep,
                         long long rows_per_batch, void* out, int ldo, long long plane_stride, int planes,
                         int bf16, cudaStream_t stream);
+/* fused, single-read form of vcr_row_lse + vcr_colsum_softmax (unmasked): out[B,n] = column sums of softmax rows */
+size_t vcr_softmax_colsum_workspace_bytes(int B, long long rows_per_batch, int ld, int n);
+int vcr_softmax_colsum(const float* S, int ld, int B, long long rows_per_batch, int n, float* out,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int vcr_colsum_softmax(const float* S, int ld, int B, long long rows_per_batch, int n, const float* rmax,
                        const float* rsum, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int vcr_rowsum(const float* P, int ld, long long rows, int n, float* out, cudaStream_t stream);

@@ -603,3 +603,20 @@ def synth_ckpt_cache():
     if "ck" not in _CK:
         _CK["ck"] = synth.make_checkpoint(1234, emb_weights=dict(load_golden("lpd_pretrained_weights")))
     return _CK["ck"]
+
+
+@pytest.mark.parametrize("B,rpb,n", [(3, 40, 333), (2, 4 * 768, 768), (2, 130, 1024), (1, 70, 4096)])
+def test_fused_softmax_colsum(B, rpb, n):
+    """Single-read fused statistic (partial-overlap key selection, model/transformer.py:35-39) vs float64, and vs the
+    two-kernel path it replaces."""
+    rs = np.random.RandomState(B + n)
+    ld = (n + 3) // 4 * 4
+    s = np.zeros((B * rpb, ld), dtype=np.float32)
+    s[:, :n] = (rs.randn(B * rpb, n) * 3).astype(np.float32)
+    S = cu(s)
+    want = np.exp(s[:, :n].astype(np.float64) - s[:, :n].max(-1, keepdims=True))
+    want = (want / want.sum(-1, keepdims=True)).reshape(B, rpb, n).sum(1)
+    got = nump(ops.colsum_softmax(S, n, B, fused=True))
+    old = nump(ops.colsum_softmax(S, n, B, fused=False))
+    assert rel_err(got, want) < 1e-5 and rel_err(old, want) < 1e-5
+    assert np.array_equal(nump(ops.colsum_softmax(S, n, B, fused=True)), got)      # deterministic

@@ -275,6 +275,51 @@ __global__ void colsum_softmax_partial_kernel(const float* __restrict__ S, int l
     part[((size_t)b * slabs + slab) * n + j] = acc;
 }
 
+// Fused partial-overlap key statistic (model/transformer.py:35-39): colsum[b, j] = sum over the rows i of batch b of
+// softmax_j(S_i*)_j, with S read from HBM ONCE: a CTA stages RB whole rows in shared memory, takes their max / sum there,
+// then one thread per column adds the normalised exponentials of its RB rows (fixed order) into a per-slab partial.
+// Deterministic: partials are reduced in slab order by colsum_final_kernel.
+__global__ void __launch_bounds__(256, 2)
+softmax_colsum_fused_kernel(const float* __restrict__ S, int ld, long long rows_per_batch, int n, int RB,
+                            float* __restrict__ part) {
+    extern __shared__ __align__(16) float fsm[];
+    float* tile = fsm;                       // [RB][ld]
+    float* rinv = fsm + (size_t)RB * ld;     // [RB]  1 / row sum
+    const int slab = blockIdx.x, b = blockIdx.y, slabs = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = (long long)slab * RB;
+    const int nr = (int)min((long long)RB, rows_per_batch - r0);
+    const float* base = S + ((long long)b * rows_per_batch + r0) * ld;
+    // the whole slab is requested up front (cp.async, 16 B per request): ~100 KB in flight per CTA, two CTAs per SM
+    const int ld4 = ld >> 2;
+    for (int e = threadIdx.x; e < nr * ld4; e += 256) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(tile + (size_t)e * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(base + (size_t)e * 4) : "memory");
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    for (int r = warp; r < nr; r += 8) {
+        float* t = tile + (size_t)r * ld;
+        float m = -INFINITY;
+        for (int j = lane; j < n; j += 32) m = fmaxf(m, t[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < n; j += 32) {
+            const float e = expf(t[j] - m);
+            t[j] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        if (lane == 0) rinv[r] = 1.f / s;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += 256) {
+        float acc = 0.f;
+        for (int r = 0; r < nr; ++r) acc = fmaf(tile[(size_t)r * ld + j], rinv[r], acc);
+        part[((size_t)b * slabs + slab) * n + j] = acc;
+    }
+}
+
 // rowsum[r] = sum_j P[r, j]   (model/vcrnet_model.py:244 after the dim=1 softmax)
 __global__ void rowsum_kernel(const float* __restrict__ P, int ld, long long rows, int n, float* __restrict__ out) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -566,6 +611,42 @@ VCR_API int vcr_colsum_softmax(const float* S, int ld, int B, long long rows_per
     VCR_CHECK_LAUNCH();
     dim3 g2(vcr_cdiv(n, 128), B);
     colsum_final_kernel<<<g2, 128, 0, stream>>>(part, slabs, n, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+static int fused_colsum_rows_per_cta(int ld) {
+    int rb = (int)((110 * 1024) / ((size_t)ld * sizeof(float) + sizeof(float)));    // two CTAs per SM
+    return rb > 64 ? 64 : rb;
+}
+VCR_API size_t vcr_softmax_colsum_workspace_bytes(int B, long long rows_per_batch, int ld, int n) {
+    const int rb = fused_colsum_rows_per_cta(ld);
+    if (rb < 1) return 0;
+    return (size_t)B * ((rows_per_batch + rb - 1) / rb) * n * sizeof(float);
+}
+// out [B, n] = per-batch column sums of the row softmax of S [B*rows_per_batch, ld] (first n columns), S read once.
+VCR_API int vcr_softmax_colsum(const float* S, int ld, int B, long long rows_per_batch, int n, float* out,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    VCR_REQUIRE(S && out && B > 0 && rows_per_batch > 0 && n > 0 && n <= ld && B <= 65535 && (ld & 3) == 0 &&
+                (reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    const int rb = fused_colsum_rows_per_cta(ld);
+    if (rb < 1) return VCR_ERR_UNSUPPORTED;
+    const long long slabs = (rows_per_batch + rb - 1) / rb;
+    if (slabs > 0x7fffffff) return VCR_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vcr_softmax_colsum_workspace_bytes(B, rows_per_batch, ld, n)) return VCR_ERR_WORKSPACE;
+    const size_t smem = ((size_t)rb * ld + rb) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(softmax_colsum_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VCR_ERR_LAUNCH;
+        configured = true;
+    }
+    float* part = reinterpret_cast<float*>(workspace);
+    dim3 g((unsigned)slabs, B);
+    softmax_colsum_fused_kernel<<<g, 256, smem, stream>>>(S, ld, rows_per_batch, n, rb, part);
+    VCR_CHECK_LAUNCH();
+    dim3 g2(vcr_cdiv(n, 128), B);
+    colsum_final_kernel<<<g2, 128, 0, stream>>>(part, (int)slabs, n, out);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }

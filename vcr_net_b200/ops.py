@@ -240,10 +240,20 @@ def softmax_operand(S: torch.Tensor, n: int, mode, keep=None, rows_per_batch=0) 
     return out
 
 
-def colsum_softmax(S: torch.Tensor, n: int, B: int):
-    """column sums per batch of softmax(S) over rows, S fp32 [B*rows_per_batch, ld] left untouched."""
+def colsum_softmax(S: torch.Tensor, n: int, B: int, fused: bool = True):
+    """column sums per batch of softmax(S) over rows, S fp32 [B*rows_per_batch, ld] left untouched.
+    fused: one kernel that reads S from HBM once (rows staged in shared memory); else row_lse + colsum_softmax."""
     rows, _, ld = _rows(S)
     dev = S.device
+    if fused:
+        L = lib()
+        wsb = L.vcr_softmax_colsum_workspace_bytes(B, rows // B, ld, n)
+        if wsb > 0:
+            out = torch.empty((B, n), dtype=_F32, device=dev)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            L.check(L.vcr_softmax_colsum(S.data_ptr(), ld, B, rows // B, n, out.data_ptr(), ws.data_ptr(), wsb,
+                                         _stream(S)), "vcr_softmax_colsum")
+            return out
     rmax = torch.empty(rows, dtype=_F32, device=dev)
     rsum = torch.empty(rows, dtype=_F32, device=dev)
     out = torch.empty((B, n), dtype=_F32, device=dev)
