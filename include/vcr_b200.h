@@ -182,6 +182,20 @@ int vcr_transpose(const float* in, float* out, int nb, int R, int C, int ld_in, 
                   long long stride_in, long long stride_out, cudaStream_t stream);
 int vcr_add(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 
+/* ---- data step + evaluation metrics on the device ------------------------------------
+ * vcr_make_pairs: util/data.py:247-309 minus the random draws (host draws pose + permutations like the reference):
+ *   src[p,:,n] = base[p, idx_src[p,n]], tgt[p,:,n] = R_p base[p, idx_tgt[p,n]] + t_p in float64 (:289-291), outputs as
+ *   fp64 [P,3,N] (input of the crop) and / or fp32.  pose [P,12] fp64 = row-major R then t.
+ * vcr_crop_nearest: util/data.py:320-329: the `keep` points nearest to the last point, nearest first -> fp32 [P,3,keep].
+ * vcr_eval_metrics: model/vcrnet_model.py:583-630 per-batch metrics accumulated into device double acc[8] =
+ *   {pose loss, cycle loss, mse_ab, mae_ab, mse_ba, mae_ba, examples, -}, each weighted by the batch size. */
+int vcr_make_pairs(const float* base, int P, int Nb, const int* idx_src, const int* idx_tgt, const double* pose,
+                   int N, double* src64, double* tgt64, float* src, float* tgt, cudaStream_t stream);
+int vcr_crop_nearest(const double* pc64, int P, int N, int keep, float* out, cudaStream_t stream);
+int vcr_eval_metrics(const float* src, const float* tgt, int N, const float* srcK, const float* corrK, int M,
+                     const float* R_gt, const float* t_gt, const float* R_ab, const float* t_ab,
+                     const float* R_ba, const float* t_ba, int B, double* acc, cudaStream_t stream);
+
 /* ---- ICP refinement (--iter=0): model/icp_model.py:26-108 ICP.forward, model/vcrnet_model.py:46-62 -----------
  * vcr_icp_nearest = nearest_neighbor (:52-75): corr [B,3,Ns] = nearest dst point per src point under
  * pd = (-xx - (-2 s.d)) - yy (ties -> lower index); *err_sum (double, caller-zeroed) += sum of the best pd.

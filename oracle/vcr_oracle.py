@@ -426,6 +426,21 @@ def vcrnet_forward(p, src, tgt, partial=False, overlap2=0.75, h=4, pointer="tran
     return (out, stages) if return_stages else out
 
 
+def eval_metrics_batch(src, tgt, srcK, corrK, R_gt, t_gt, R_ab, t_ab, R_ba, t_ba):
+    """One batch of test_one_epoch's running sums (model/vcrnet_model.py:589-627), each already times batch_size:
+    (loss_pose, cycle_loss, mse_ab, mae_ab, mse_ba, mae_ba, batch_size)."""
+    B = src.shape[0]
+    eye = np.eye(3, dtype=np.float64)[None]
+    t_target = transform_point_cloud(tgt, R_ba, t_ba).astype(np.float64)                  # :589
+    t_srcK = transform_point_cloud(srcK, R_gt, t_gt).astype(np.float64)                   # :591
+    loss_pose = ((np.matmul(R_ab.transpose(0, 2, 1), R_gt).astype(np.float64) - eye) ** 2).mean() \
+        + ((t_ab.astype(np.float64) - t_gt) ** 2).mean()                                  # :614-615
+    rot = ((np.matmul(R_ba, R_ab).astype(np.float64) - eye) ** 2).mean()                  # :620
+    tr = ((np.matmul(R_ba.transpose(0, 2, 1), t_ab[:, :, None])[:, :, 0].astype(np.float64) + t_ba) ** 2).mean()
+    return (loss_pose * B, (rot + tr) * B, ((t_srcK - corrK) ** 2).mean() * B, np.abs(t_srcK - corrK).mean() * B,
+            ((t_target - src) ** 2).mean() * B, np.abs(t_target - src).mean() * B, B)
+
+
 def icp_forward(src_init, dst, max_iterations=10, tolerance=0.001):
     """ICP.forward (model/icp_model.py:26-50) -> (srcInit, src, R_ab, t_ab, R_ba, t_ba, iterations)."""
     src_init, dst = _f32(src_init), _f32(dst)

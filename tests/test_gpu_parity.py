@@ -620,3 +620,55 @@ def test_fused_softmax_colsum(B, rpb, n):
     old = nump(ops.colsum_softmax(S, n, B, fused=False))
     assert rel_err(got, want) < 1e-5 and rel_err(old, want) < 1e-5
     assert np.array_equal(nump(ops.colsum_softmax(S, n, B, fused=True)), got)      # deterministic
+
+
+def test_vcrnet_iter_target_embedding_reuse_is_bit_identical(net_partial):
+    """config.reuse_target_embedding hoists the loop-invariant emb_nn(tgt) out of the --iter loop: same bits out."""
+    from vcr_net_b200 import config
+    p = synth.make_pairs(3, 512, partial=True, first_item=21)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    base = V.vcrnetIter(net_partial, src, tgt, iter=3)
+    config.reuse_target_embedding = True
+    try:
+        again = V.vcrnetIter(net_partial, src, tgt, iter=3)
+    finally:
+        config.reuse_target_embedding = False
+    for a, b in zip(base, again):
+        assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- SURVEY 8(f) row 2: data step + metrics -------------
+@pytest.mark.parametrize("partial,aligned", [(False, False), (True, False), (False, True)])
+def test_device_data_step_matches_host_generator(partial, aligned):
+    """PairGenerator (device gather + fp64 transform + nearest-to-last crop) vs oracle/synth.make_pairs, the host
+    restatement of util/data.py:247-329: identical fp32 clouds, same order."""
+    from vcr_net_b200.data import PairGenerator
+    n_items, first, N = 6, 3, 512
+    base = np.random.RandomState(1234).rand(first + n_items, 2048, 3).astype(np.float32) - 0.5   # synth.make_pairs' base
+    gen = PairGenerator(cu(base), num_points=N, partial=partial, reserve=synth.RESERVE_0575, aligned=aligned)
+    got = gen.batch(range(first, first + n_items))
+    want = synth.make_pairs(n_items, N, partial=partial, reserve=synth.RESERVE_0575, first_item=first, aligned=aligned)
+    assert tuple(got["src"].shape) == want["src"].shape
+    for k in ("src", "tgt"):
+        d = np.abs(nump(got[k]) - want[k])
+        assert d.max() <= 6e-8, (k, d.max())                       # fp64 transform, <= 1 fp32 ulp after the cast
+        assert (d > 0).mean() < 1e-3
+    assert np.allclose(nump(got["R_ab"]), want["R_ab"], atol=1e-7) and np.allclose(nump(got["t_ab"]), want["t_ab"], atol=1e-7)
+    assert np.allclose(nump(got["euler_ab"]), want["euler_ab"], atol=1e-7)
+
+
+def test_eval_accumulator_vs_oracle(net_whole):
+    from vcr_net_b200.data import EvalAccumulator
+    acc = EvalAccumulator(DEV)
+    want = np.zeros(7)
+    for first in (0, 4):
+        p = synth.make_pairs(4, 256, first_item=first)
+        src, tgt = cu(p["src"]), cu(p["tgt"])
+        out = V.vcrnetIter(net_whole, src, tgt, iter=1)
+        acc.update(src, tgt, out[0], out[1], cu(p["R_ab"]), cu(p["t_ab"]), out[2], out[3], out[4], out[5])
+        want += np.array(O.eval_metrics_batch(p["src"], p["tgt"], nump(out[0]), nump(out[1]), p["R_ab"], p["t_ab"],
+                                              nump(out[2]), nump(out[3]), nump(out[4]), nump(out[5])), dtype=np.float64)
+    res = acc.result()
+    assert res["num_examples"] == 8
+    for i, k in enumerate(acc.KEYS):
+        assert abs(res[k] - want[i] / 8) <= 1e-5 * max(abs(want[i] / 8), 1e-6), (k, res[k], want[i] / 8)

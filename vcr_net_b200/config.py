@@ -12,6 +12,10 @@ precision = os.environ.get("VCR_PRECISION", "h3")
 VALID = ("fp32", "h3", "fp16", "bf16")
 # flash attention kernel (attn_tc.cu) vs materialised scores through the GEMM kernel (tensor-core modes only)
 flash_attention = os.environ.get("VCR_FLASH", "1") != "0"
+# vcrnetIter: compute the loop-invariant target embedding emb_nn(tgt) once per call instead of once per --iter iteration
+# (bit-identical outputs).  Off by default so the default path does exactly the work the reference does per iteration;
+# bench.py reports the throughput with the switch on as a separate, labelled field.
+reuse_target_embedding = os.environ.get("VCR_REUSE_TGT_EMB", "0") == "1"
 
 
 def set_precision(p: str):

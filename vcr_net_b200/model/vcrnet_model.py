@@ -13,12 +13,24 @@ from .transformer import Transformer
 
 
 def vcrnetIter(net, src, tgt, iter=1):
-    """model/vcrnet_model.py:21-43: refine `iter` times, composing R_f <- R_i R_f, t_f <- R_i t_f + t_i."""
+    """model/vcrnet_model.py:21-43: refine `iter` times, composing R_f <- R_i R_f, t_f <- R_i t_f + t_i.
+
+    The target cloud never changes inside the loop, so its embedding ``emb_nn(tgt)`` is loop-invariant: with
+    ``config.reuse_target_embedding`` (default off) it is computed once per call and handed to every iteration instead of
+    being recomputed ``iter`` times as the reference does (:27).  Outputs are bit-identical either way."""
+    from .. import config
     transformed_src = src
     R_f = t_f = None
     srcK = src_corrK = None
+    tgt_tok = None
+    if iter > 1 and config.reuse_target_embedding and isinstance(net, VCRNet):
+        with torch.no_grad():
+            tgt_tok = net.emb_nn.forward_tokens(tgt.contiguous())
     for _ in range(iter):
-        srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt)
+        if tgt_tok is not None:
+            srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt, tgt_tokens=tgt_tok)
+        else:
+            srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt)
         transformed_src = ops.rigid_apply(transformed_src, R, t)
         if R_f is None:
             R_f, t_f = R.detach().clone(), t.detach().clone()
@@ -201,11 +213,13 @@ class VCRNet(nn.Module):
         self.svd = SVDHead(args=args)
 
     @torch.no_grad()      # registration INFERENCE path: only the LPD pre-training path (LPD / LPDNet) has a backward
-    def forward(self, *input, stages=None):
+    def forward(self, *input, stages=None, tgt_tokens=None):
         src, tgt = input[0].contiguous(), input[1].contiguous()
         B = src.shape[0]
         same = src.shape == tgt.shape
-        if same:                                           # both clouds through ONE batch of 2B
+        if tgt_tokens is not None:                         # loop-invariant target embedding supplied by vcrnetIter
+            src_tok, tgt_tok = self.emb_nn.forward_tokens(src), tgt_tokens
+        elif same:                                         # both clouds through ONE batch of 2B
             emb = self.emb_nn.forward_tokens(torch.cat([src, tgt], dim=0))
             src_tok, tgt_tok = emb[:B], emb[B:]
         else:
