@@ -362,6 +362,9 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         d["ms"] += ms; d["n"] += 1
         if name in ("vcr_gemm_f32", "vcr_gemm_tc"):
             d["flops"] += gemm_flops(args)
+        elif name == "vcr_flash_attn_tc":                  # 4 * Nq * Nk * dk per (batch, head): QK^T + PV
+            Bq, Hq, Nq, Nk, dk = args[9:14]
+            d["flops"] += 4.0 * Nq * Nk * dk * Bq * Hq
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     peaks = {}
     try:
@@ -378,7 +381,7 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     if top[1]["flops"] > 0:
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12
-        passes = 3 if (a.precision == "h3" and top[0] == "vcr_gemm_tc") else 1
+        passes = 3 if (a.precision == "h3" and top[0] in ("vcr_gemm_tc", "vcr_flash_attn_tc")) else 1
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                     tensor_passes_per_product=passes, tensor_work_frac=passes * ach / peak,
