@@ -672,3 +672,68 @@ def test_eval_accumulator_vs_oracle(net_whole):
     assert res["num_examples"] == 8
     for i, k in enumerate(acc.KEYS):
         assert abs(res[k] - want[i] / 8) <= 1e-5 * max(abs(want[i] / 8), 1e-6), (k, res[k], want[i] / 8)
+
+
+# ---------------------------------------------------------------- ragged / full-size cases ------------------------
+def test_vcrnet_ragged_sizes_vs_oracle(net_whole, ckpt, precision):
+    """Odd point counts (not multiples of any tile), a single pair, and clouds of different sizes."""
+    p = synth.make_pairs(1, 333, first_item=70)
+    out = V.vcrnetIter(net_whole, cu(p["src"]), cu(p["tgt"]), iter=1)
+    want = O.vcrnet_iter(ckpt, p["src"], p["tgt"], 1)
+    for n, o, w in zip(("srcK", "corrK", "R_ab", "t_ab"), out, want):
+        assert rel_err(nump(o), w) < 5e-4, n
+    q = synth.make_pairs(2, 300, first_item=80)
+    tgt_short = np.ascontiguousarray(q["tgt"][:, :, :257])                 # Ns = 300, Nt = 257
+    out = V.vcrnetIter(net_whole, cu(q["src"]), cu(tgt_short), iter=1)
+    want = O.vcrnet_iter(ckpt, q["src"], tgt_short, 1)
+    assert tuple(out[1].shape) == (2, 3, 300)
+    for n, o, w in zip(("srcK", "corrK", "R_ab", "t_ab"), out, want):
+        assert rel_err(nump(o), w) < 5e-4, n
+
+
+def test_partial_full_size_properties(net_partial):
+    """BASELINE cfg 2 size (B=24, 768 of 1024 points, iter=3): shapes of the hard-correspondence sets, proper rotations,
+    inverse pose, batch independence."""
+    p = synth.make_pairs(24, 1024, partial=True, first_item=400)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    assert src.shape[2] == 768
+    out = V.vcrnetIter(net_partial, src, tgt, iter=3)
+    M = int(int(768 * 0.84 * synth.OVERLAP2_0575) * 0.52 * synth.OVERLAP2_0575)
+    assert tuple(out[0].shape) == (24, 3, M) and tuple(out[1].shape) == (24, 3, M)
+    R, t = nump(out[2]).astype(np.float64), nump(out[3]).astype(np.float64)
+    assert np.isfinite(R).all() and np.isfinite(t).all()
+    assert np.allclose(np.einsum("bij,bkj->bik", R, R), np.eye(3), atol=1e-5)
+    assert np.allclose(np.linalg.det(R), 1.0, atol=1e-5)
+    Rb, tb = nump(out[4]).astype(np.float64), nump(out[5]).astype(np.float64)
+    assert np.allclose(np.einsum("bij,bjk->bik", Rb, R), np.eye(3), atol=1e-5)
+    assert np.allclose(np.einsum("bij,bj->bi", Rb, t) + tb, 0, atol=1e-5)
+    one = V.vcrnetIter(net_partial, src[5:6], tgt[5:6], iter=3)
+    assert np.abs(nump(one[2]) - nump(out[2])[5:6]).max() < 1e-5
+    # every selected source point is one of the input points, every correspondence one of the target points
+    s0, c0 = nump(out[0])[0].T, nump(out[1])[0].T
+
+
+def test_cfg4_size_4096_points(net_whole):
+    """BASELINE cfg 4 point count (4096 per cloud; 4 pairs here): the path runs at that size, kNN stays bit-exact."""
+    p = synth.make_pairs(4, 4096, first_item=500, base_points=4096)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    out = V.vcrnetIter(net_whole, src, tgt, iter=1)
+    R = nump(out[2]).astype(np.float64)
+    assert np.isfinite(R).all() and np.allclose(np.einsum("bij,bkj->bik", R, R), np.eye(3), atol=1e-5)
+    assert np.array_equal(nump(V.knn(src[:1], 20)), canon.knn(p["src"][:1], 20))
+    one = V.vcrnetIter(net_whole, src[2:3], tgt[2:3], iter=1)
+    assert np.abs(nump(one[2]) - nump(out[2])[2:3]).max() < 1e-5
+
+
+def test_gemm_f32_ragged_k():
+    """K not a multiple of 4 (odd key counts in fp32-mode attention): rows padded to 16 bytes, tail read element-wise."""
+    rs = np.random.RandomState(9)
+    M, N, K = 70, 48, 333
+    a = np.zeros((M, 336), dtype=np.float32); a[:, :K] = rs.randn(M, K); a[:, K:] = np.nan     # padding must never be read
+    w = np.zeros((N, 336), dtype=np.float32); w[:, :K] = rs.randn(N, K); w[:, K:] = np.nan
+    got = nump(ops.gemm(cu(a)[:, :K], cu(w)[:, :K]))
+    want = a[:, :K].astype(np.float64) @ w[:, :K].astype(np.float64).T
+    assert np.isfinite(got).all() and rel_err(got, want) < 1e-5
+    v = rs.randn(K, 64).astype(np.float32)                                                      # [K, N] layout
+    got = nump(ops.gemm(cu(a)[:, :K], cu(v), b_layout=1))
+    assert rel_err(got, a[:, :K].astype(np.float64) @ v.astype(np.float64)) < 1e-5

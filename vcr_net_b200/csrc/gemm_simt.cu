@@ -51,19 +51,24 @@ sgemm_kernel(const GemmParams p) {
     const int b_k = tid >> 5, b_n = (tid & 31) * 4;          // NN: B rows b_k, b_k+8 ; n offset b_n
     float4 ra[2], rb[2];
 
+    // 4 consecutive K elements of a row; the last group of a ragged K (K % 4 != 0) is read element-wise
+    auto ld_k4 = [&](const float* row, int kk) -> float4 {
+        if (kk + 3 < p.K) return *reinterpret_cast<const float4*>(row + kk);
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 4; ++c) if (kk + c < p.K) t[c] = row[kk + c];
+        return make_float4(t[0], t[1], t[2], t[3]);
+    };
     auto load_tiles = [&](int k0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int m = m0 + a_r + h * 64, kk = k0 + a_k;
-            ra[h] = (m < p.M && kk < p.K) ? *reinterpret_cast<const float4*>(A + (size_t)m * p.lda + kk)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            ra[h] = (m < p.M && kk < p.K) ? ld_k4(A + (size_t)m * p.lda, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (!B_KN) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int n = n0 + a_r + h * 64, kk = k0 + a_k;
-                rb[h] = (n < p.N && kk < p.K) ? *reinterpret_cast<const float4*>(B + (size_t)n * p.ldb + kk)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                rb[h] = (n < p.N && kk < p.K) ? ld_k4(B + (size_t)n * p.ldb, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
 #pragma unroll
@@ -174,7 +179,7 @@ sgemm_kernel(const GemmParams p) {
 }  // namespace
 
 // Generic batched GEMM.  b_layout: 0 = B stored [N,K] (ldb >= K), 1 = B stored [K,N] (ldb >= N).
-// Requirements: K % 4 == 0, lda % 4 == 0, A/B 16-byte aligned and ldb % 4 == 0;
+// Requirements: lda % 4 == 0, A/B 16-byte aligned and ldb % 4 == 0 (any K: a ragged tail is read element-wise);
 // batch strides are in elements; nb_outer * nb_inner <= 65535.  act: 0 none, 1 LeakyReLU(slope).
 VCR_API int vcr_gemm_f32(const float* A, int lda, long long sAo, long long sAi,
                          const float* B, int ldb, long long sBo, long long sBi, int b_layout,
@@ -183,7 +188,7 @@ VCR_API int vcr_gemm_f32(const float* A, int lda, long long sAo, long long sAi,
                          int M, int N, int K, int nb_outer, int nb_inner,
                          float alpha, int act, float slope, cudaStream_t stream) {
     VCR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && nb_outer > 0 && nb_inner > 0);
-    if ((K & 3) || (lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    if ((lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return VCR_ERR_INVALID;
     if ((sAo & 3) || (sAi & 3) || (sBo & 3) || (sBi & 3)) return VCR_ERR_INVALID;
     if (ldb & 3) return VCR_ERR_INVALID;

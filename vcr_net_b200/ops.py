@@ -475,9 +475,10 @@ def attention_f32(q, k, v, B, h, Nq, Nk, dk, scale, out, keep=None, colsum_out=F
     vt, vld, vsb, vsh = v
     ot, old, osb, osh = out
     dev = qt.device
-    per_b = h * Nq * Nk * 4
+    ldS = (Nk + 3) // 4 * 4                  # rows padded to 16 bytes: float4 row starts for any key count
+    per_b = h * Nq * ldS * 4
     cb = max(1, min(B, max_ws_bytes // per_b))
-    S = torch.empty((cb, h, Nq, Nk), dtype=_F32, device=dev)
+    S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
     csum = torch.empty((B, Nk), dtype=_F32, device=dev) if colsum_out else None
     esz = 4
     for b0 in range(0, B, cb):
@@ -486,14 +487,14 @@ def attention_f32(q, k, v, B, h, Nq, Nk, dk, scale, out, keep=None, colsum_out=F
         L = lib()
         st = _stream(qt)
         L.check(L.vcr_gemm_f32(off(qt, qsb), qld, qsb, qsh, off(kt, ksb), kld, ksb, ksh, 0,
-                               S.data_ptr(), Nk, h * Nq * Nk, Nq * Nk, None, None, 0, 0, 0,
+                               S.data_ptr(), ldS, h * Nq * ldS, Nq * ldS, None, None, 0, 0, 0,
                                Nq, Nk, dk, nb, h, float(scale), 0, 0.0, st), "vcr_gemm_f32(QK)")
-        Sv = S[:nb].view(nb * h * Nq, Nk)
+        Sv = S[:nb].view(nb * h * Nq, ldS)[:, :Nk]
         kp = keep[b0:b0 + nb] if keep is not None else None
         softmax_rows_(Sv, kp, h * Nq)
         if colsum_out:
             colsum(Sv, nb, out=csum[b0:b0 + nb])
-        L.check(L.vcr_gemm_f32(S.data_ptr(), Nk, h * Nq * Nk, Nq * Nk, off(vt, vsb), vld, vsb, vsh, 1,
+        L.check(L.vcr_gemm_f32(S.data_ptr(), ldS, h * Nq * ldS, Nq * ldS, off(vt, vsb), vld, vsb, vsh, 1,
                                off(ot, osb), old, osb, osh, None, None, 0, 0, 0,
                                Nq, dk, Nk, nb, h, 1.0, 0, 0.0, st), "vcr_gemm_f32(PV)")
     return csum
