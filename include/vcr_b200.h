@@ -155,7 +155,8 @@ int vcr_sqnorm_rows(const float* X, int ld, long long rows, int D, float* out, c
 int vcr_softcorr_rows(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
                       const float* tgt, int mode, float* corr, int* best_idx, float* best_val, cudaStream_t stream);
 int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy, cudaStream_t stream);
-/* row sums of the softmax taken over sources (dim=1) (:243-244); workspace 2*B*Nt floats. */
+/* row sums of the softmax taken over sources (dim=1) (:243-244); workspace from the size query. */
+size_t vcr_rowsum_colsoftmax_workspace_bytes(int B, int Nt);
 int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
 int vcr_gather_rows(const float* in, int ld_in, int B, int Nin, const int* idx, int K, int C, float* out,

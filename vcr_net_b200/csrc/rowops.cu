@@ -413,18 +413,36 @@ __global__ void softcorr_rows_kernel(float* __restrict__ dot, int ld, int Ns, in
 // column softmax statistics for selectCom's second pass (model/vcrnet_model.py:243-244):
 //   rowsum_i = sum_j softmax over i (dim=1) of pd_ij.  Needs column max and column sum-exp first.
 // Thread-per-column kernels over the pd matrix (coalesced along j).
-__global__ void col_lse_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt,
-                               float* __restrict__ cmax, float* __restrict__ csum) {
-    const int b = blockIdx.y;
+// Column statistics are split over row slabs so that the whole GPU works on a [Ns, Nt] matrix (a thread-per-column
+// kernel walking all Ns rows leaves 97 % of the SMs idle): slab maxima, then slab sums of exp(v - column max), each
+// reduced in slab order (deterministic).
+constexpr int COL_SLABS = 24;
+__global__ void col_max_partial_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt, float* __restrict__ pmax) {
+    const int b = blockIdx.z, slab = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Nt) return;
+    const int per = (Ns + COL_SLABS - 1) / COL_SLABS;
+    const int i0 = slab * per, i1 = min(Ns, i0 + per);
     const float* p = pd + (size_t)b * Ns * ld + j;
     float m = -INFINITY;
-    for (int i = 0; i < Ns; ++i) m = fmaxf(m, p[(size_t)i * ld]);
+    for (int i = i0; i < i1; ++i) m = fmaxf(m, p[(size_t)i * ld]);
+    pmax[((size_t)b * COL_SLABS + slab) * Nt + j] = m;
+}
+__global__ void col_sum_partial_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt,
+                                       const float* __restrict__ pmax, float* __restrict__ cmax,
+                                       float* __restrict__ psum) {
+    const int b = blockIdx.z, slab = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Nt) return;
+    float m = -INFINITY;
+    for (int t = 0; t < COL_SLABS; ++t) m = fmaxf(m, pmax[((size_t)b * COL_SLABS + t) * Nt + j]);
+    if (slab == 0) cmax[(size_t)b * Nt + j] = m;
+    const int per = (Ns + COL_SLABS - 1) / COL_SLABS;
+    const int i0 = slab * per, i1 = min(Ns, i0 + per);
+    const float* p = pd + (size_t)b * Ns * ld + j;
     float s = 0.f;
-    for (int i = 0; i < Ns; ++i) s += expf(p[(size_t)i * ld] - m);
-    cmax[(size_t)b * Nt + j] = m;
-    csum[(size_t)b * Nt + j] = s;
+    for (int i = i0; i < i1; ++i) s += expf(p[(size_t)i * ld] - m);
+    psum[((size_t)b * COL_SLABS + slab) * Nt + j] = s;
 }
 __global__ void rowsum_colsoftmax_kernel(const float* __restrict__ pd, int ld, int Ns, int Nt,
                                          const float* __restrict__ cmax, const float* __restrict__ csum,
@@ -689,15 +707,25 @@ VCR_API int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* 
     return VCR_OK;
 }
 
-// rowsum of the column-softmax of pd (workspace: 2*B*Nt floats)
+VCR_API size_t vcr_rowsum_colsoftmax_workspace_bytes(int B, int Nt) {
+    return (size_t)(2 + 2 * COL_SLABS) * B * Nt * sizeof(float);
+}
+// rowsum of the column-softmax of pd (workspace: vcr_rowsum_colsoftmax_workspace_bytes)
 VCR_API int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,
                                   size_t workspace_bytes, cudaStream_t stream) {
     VCR_REQUIRE(pd && out && B > 0 && Ns > 0 && Nt > 0 && B <= 65535);
-    if (!workspace || workspace_bytes < (size_t)2 * B * Nt * sizeof(float)) return VCR_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < vcr_rowsum_colsoftmax_workspace_bytes(B, Nt)) return VCR_ERR_WORKSPACE;
     float* cmax = reinterpret_cast<float*>(workspace);
     float* csum = cmax + (size_t)B * Nt;
-    dim3 g(vcr_cdiv(Nt, 64), B);
-    col_lse_kernel<<<g, 64, 0, stream>>>(pd, ld, Ns, Nt, cmax, csum);
+    float* pmax = csum + (size_t)B * Nt;
+    float* psum = pmax + (size_t)COL_SLABS * B * Nt;
+    dim3 g(vcr_cdiv(Nt, 128), COL_SLABS, B);
+    col_max_partial_kernel<<<g, 128, 0, stream>>>(pd, ld, Ns, Nt, pmax);
+    VCR_CHECK_LAUNCH();
+    col_sum_partial_kernel<<<g, 128, 0, stream>>>(pd, ld, Ns, Nt, pmax, cmax, psum);
+    VCR_CHECK_LAUNCH();
+    dim3 g1(vcr_cdiv(Nt, 128), B);
+    colsum_final_kernel<<<g1, 128, 0, stream>>>(psum, COL_SLABS, Nt, csum);
     VCR_CHECK_LAUNCH();
     dim3 g2(vcr_cdiv(Ns, 8), B);
     rowsum_colsoftmax_kernel<<<g2, 256, 0, stream>>>(pd, ld, Ns, Nt, cmax, csum, out);

@@ -551,8 +551,8 @@ def negdist_(dot, ld, Ns, Nt, xx, yy):
 def rowsum_colsoftmax(pd, ld, Ns, Nt):
     B = pd.shape[0]
     out = torch.empty((B, Ns), dtype=_F32, device=pd.device)
-    ws = torch.empty(2 * B * Nt, dtype=_F32, device=pd.device)
     L = lib()
+    ws = torch.empty(L.vcr_rowsum_colsoftmax_workspace_bytes(B, Nt) // 4, dtype=_F32, device=pd.device)
     L.check(L.vcr_rowsum_colsoftmax(pd.data_ptr(), ld, B, Ns, Nt, out.data_ptr(), ws.data_ptr(), ws.numel() * 4,
                                     _stream(pd)), "vcr_rowsum_colsoftmax")
     return out
