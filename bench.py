@@ -13,7 +13,7 @@ in the default line under "other_workloads".
   value     pairs/s with inputs resident in HBM, CUDA events per step, L2 flushed between steps
   e2e       same metric through the public module API from pinned HOST buffers (H2D + D2H timed)
   roofline  dominant kernel: algorithmic FLOP/launch / CUDA-event launch time vs MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (numpy restatement of the reference) on this box's host cores,
+  cpu_baseline  the oracle port on torch CPU operators (oracle/vcr_oracle_torch.py) on this box's host cores,
                 bounded sample; `--impl reference` makes that the measured arm.
 """
 from __future__ import annotations
@@ -75,24 +75,32 @@ def load_ckpt():
 # ------------------------------------------------------------------------------------------------
 
 def cpu_pairs_per_sec(cfg, num_points, n_pairs, repeats=1):
+    """The CPU arm: oracle/vcr_oracle_torch.py, the registration loop restated on torch CPU operators (the ATen kernels
+    the reference itself runs) with all intra-op threads.  The reference is Python/torch and cannot travel to the GPU box."""
+    import torch
     from oracle import synth
-    from oracle import vcr_oracle as O
+    from oracle import vcr_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count())
     ckpt = load_ckpt()
     p = synth.make_pairs(n_pairs, num_points, partial=cfg["partial"], reserve=cfg["reserve"] if cfg["partial"] else 1.0)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        O.vcrnet_iter(ckpt, p["src"], p["tgt"], cfg["iters"], partial=cfg["partial"], overlap2=cfg["overlap2"])
+        OT.vcrnet_iter(ckpt, p["src"], p["tgt"], cfg["iters"], partial=cfg["partial"], overlap2=cfg["overlap2"])
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_pairs / best, best
+
+
+CPU_ARM = ("oracle/vcr_oracle_torch.py: the reference's registration loop restated on torch CPU operators (same ATen "
+           "kernels, fp32, all host threads); parity-checked against the live-reference golden vectors")
 
 
 def run_reference_arm(a, cfg, rank, world):
     if rank != 0:
         return
     times = []
-    n = 2                                   # bounded per-step sample so K + W steps end within minutes
+    n = 6                                   # bounded per-step sample so K + W steps end within minutes
     for i in range(a.warmup + a.steps):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, n)
         if i >= a.warmup:
@@ -105,11 +113,10 @@ def run_reference_arm(a, cfg, rank, world):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "batch_per_gpu": n, "num_points": a.num_points, "iter": cfg["iters"],
-                   "precision": "fp32 (numpy)", "parallelism": "host cores of rank 0 only",
-                   "note": "bounded sample: 2 pairs per step instead of the GPU arm's batch"},
+                   "precision": "fp32 (torch CPU)", "parallelism": "host cores of rank 0 only",
+                   "note": "bounded sample: 6 pairs per step instead of the GPU arm's batch"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} pairs per step through oracle/vcr_oracle.py (numpy restatement of the "
-                                   f"reference; the reference is Python/torch and cannot travel to this box)"},
+                         "sample": f"{n} pairs per step through {CPU_ARM}"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -417,9 +424,7 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     if not a.no_cpu_baseline and not cfg.get("train"):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, a.cpu_sample_pairs)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{a.cpu_sample_pairs} pairs of the same workload, one pass of "
-                                          f"oracle/vcr_oracle.py (numpy restatement of the reference, BLAS threads = all "
-                                          f"{os.cpu_count()} cores), {dt:.1f} s"}
+                                "sample": f"{a.cpu_sample_pairs} pairs of the same workload, one pass ({dt:.1f} s) of {CPU_ARM}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -437,7 +442,7 @@ def main():
                                   str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
     cfg = workload_cfg(a)
     if a.cpu_sample_pairs <= 0:
-        a.cpu_sample_pairs = 6 if cfg["partial"] else 12
+        a.cpu_sample_pairs = 12 if cfg["partial"] else 24
     if a.impl == "reference":
         run_reference_arm(a, cfg, rank, world)
     else:
