@@ -138,7 +138,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:

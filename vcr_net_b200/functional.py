@@ -151,30 +151,48 @@ class LPDNetTrainFn(torch.autograd.Function):
         B, N, _ = emb.shape
         T = B * N
         g_emb = g_emb.contiguous()
+        tc = config.precision != "fp32"
+
+        def mm(a, w, bias=None, residual=None):
+            """a [M,K] @ w[N,K]^T (+bias, +residual): SIMT fp32, or the 3-term tcgen05 GEMM (fp32-equivalent) in TC modes."""
+            if not tc or a.shape[-1] % 8 or w.shape[0] % 4:
+                return ops.gemm(a, w, bias, residual=residual)
+            M, K = a.shape[0], a.shape[1]
+            out = torch.empty((M, w.shape[0]), dtype=_F32, device=a.device)
+            ops.gemm_tc(ops.to_operand(a, "h3"), ops.to_operand(w, "h3"), M, w.shape[0], K, bias=bias, c=out,
+                        residual=residual)
+            return out
+
+        def dgrad(g, w):
+            """g [M,Nout] @ w[Nout,Nin]: data gradient of y = x w^T."""
+            if not tc:
+                return ops.gemm(g, w, b_layout=1)
+            return mm(g, w.t().contiguous())
+
         # conv3_lpd (:134-135)
         g_z3 = ops.act_bwd(g_emb.view(T, -1), emb.view(T, -1), slope)
         gW3, gb3 = ops.wgrad(g_z3, cat.view(T, 512))
-        g_cat = ops.gemm(g_z3, W["w3"], b_layout=1).view(B, N, 512)
+        g_cat = dgrad(g_z3, W["w3"]).view(B, N, 512)
         # convSN1 + max (:130-132)
         g_pq3 = torch.zeros((B, N, 512), dtype=_F32, device=emb.device)
         ops.gather_max_bwd(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_x, slope, g_cat[:, :, 256:512],
                            g_pq3[:, :, 0:256], g_pq3[:, :, 256:512])
         gWsn, gbsn = ops.wgrad(g_pq3.view(T, 512), cat[:, :, 128:256])
-        g_x2 = ops.gemm(g_pq3.view(T, 512), W["sn1_w"], b_layout=1, residual=g_cat[:, :, 128:256]).view(B, N, 128)
+        g_x2 = (dgrad(g_pq3.view(T, 512), W["sn1_w"]) + g_cat[:, :, 128:256].reshape(T, 128)).view(B, N, 128)
         # convDG2 + max (:125-126), convDG1 + max (:123-124)
         e1 = ops.edge_gather_act(pq1, idx_f, slope)                            # [T*k,128]
-        z2 = ops.gemm(e1, W["dg2_w"], W["dg2_b"])
+        z2 = mm(e1, W["dg2_w"], W["dg2_b"])
         ops.edge_max_bwd_(z2, g_x2, k, slope)                                  # z2 <- g_z2
         gWdg2, gbdg2 = ops.wgrad(z2, e1)
-        g_e1 = ops.gemm(z2, W["dg2_w"], b_layout=1)
+        g_e1 = dgrad(z2, W["dg2_w"])
         g_pq1 = ops.edge_bwd_scatter(e1, g_e1, g_cat[:, :, 0:128], idx_f, slope)
         del e1, z2, g_e1
         gWdg1, gbdg1 = ops.wgrad(g_pq1.view(T, 256), h2.view(T, 64))
-        g_h2 = ops.gemm(g_pq1.view(T, 256), W["dg1_w"], b_layout=1)
+        g_h2 = dgrad(g_pq1.view(T, 256), W["dg1_w"])
         # conv2_lpd, conv1_lpd (:111-112)
         g_z2 = ops.act_bwd(g_h2, h2.view(T, 64), slope)
         gW2, gb2 = ops.wgrad(g_z2, h1.view(T, 64))
-        g_h1 = ops.gemm(g_z2, W["w2"], b_layout=1)
+        g_h1 = dgrad(g_z2, W["w2"])
         g_z1 = ops.act_bwd(g_h1, h1.view(T, 64), slope)
         gW1, gb1 = ops.wgrad(g_z1, xyz_t.view(T, 3))
 
