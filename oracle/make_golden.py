@@ -281,9 +281,45 @@ def make_variants(ref=None):
     save("variants", **out)
 
 
+def make_tnet(ref=None):
+    """LPDNet with --t3d / --tfea TranformNets (model/lpdnet_model.py:19-70, 107-118), eval
+    mode, from the live reference.  BatchNorm statistics are randomised so the folding is exercised; the neighbour sets
+    the reference's forward used are recomputed with the reference's own knn on the reference's intermediates."""
+    torch.set_num_threads(1)
+    if ref is None:
+        ref = ref_harness.import_reference()
+    LP, U = ref.lpdnet_model, ref.util
+    out = {}
+    x = synth.make_pairs(2, 256, first_item=140)["src"]
+    with torch.no_grad():
+        for name, t3d, tfea in (("both", True, True), ("t3d", True, False)):
+            net = LP.LPDNet(ref_harness.default_args(t3d=t3d, tfea=tfea, emb_dims=128), negative_slope=0.0).eval()
+            sd = synth.make_tnet_lpdnet_weights(21, t3d, tfea, 128)        # weights are reproducible, not stored
+            ref_keys = [k for k in net.state_dict().keys() if "num_batches_tracked" not in k]
+            assert ref_keys == list(sd.keys()), "synthetic TranformNet key order != reference"
+            net.load_state_dict(synth.checkpoint_to_torch(sd), strict=False)
+            out[f"{name}.keys"] = np.array(list(net.state_dict().keys()))
+            xt = T(x)
+            trans = net.t_net3d(xt)
+            h = torch.bmm(xt.transpose(2, 1), trans).transpose(2, 1)
+            h = F.leaky_relu(net.conv2_lpd(F.leaky_relu(net.conv1_lpd(h), 0.0)), 0.0)
+            out[f"{name}.trans"] = N_(trans)
+            if tfea:
+                tf = net.t_net_fea(h)
+                h = torch.bmm(h.transpose(2, 1), tf).transpose(2, 1)
+                out[f"{name}.trans_feat"] = N_(tf)
+            out[f"{name}.idx_feat"] = N_(U.knn(h.contiguous(), 20)).astype(np.int32)
+            out[f"{name}.out"] = N_(net(xt))
+        out["x"] = x
+        out["idx_xyz"] = N_(U.knn(T(x), 20)).astype(np.int32)
+    save("tnet", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         make_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tnet":
+        make_tnet()
     elif len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
         make_lpd_train()
     else:

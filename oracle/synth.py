@@ -216,3 +216,37 @@ def make_checkpoint(seed: int = 1234, emb_dims: int = 512, ff_dims: int = 1024,
 def checkpoint_to_torch(sd):
     import torch
     return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v)).clone()) for k, v in sd.items())
+
+
+def make_tnet_lpdnet_weights(seed: int, t3d: bool = True, tfea: bool = True, emb_dims: int = 128):
+    """LPDNet(t3d, tfea) state_dict (model/lpdnet_model.py:19-42, 78-99 key order, num_batches_tracked omitted) from a
+    numpy RandomState: nn default-style uniform weights, randomised BatchNorm1d statistics / affine parameters."""
+    rs = np.random.RandomState(seed)
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def conv(name, co, ci, extra):
+        w, b = _linear_init(rs, co, ci)
+        sd[f"{name}.weight"] = w.reshape((co, ci) + extra)
+        sd[f"{name}.bias"] = b
+
+    conv("convDG1.0", 128, 128, (1, 1))
+    conv("convDG2.0", 128, 128, (1, 1))
+    conv("convSN1.0", 256, 256, (1, 1))
+    conv("conv1_lpd", 64, 3, (1,))
+    conv("conv2_lpd", 64, 64, (1,))
+    conv("conv3_lpd", emb_dims, 512, (1,))
+    for on, name, k in ((t3d, "t_net3d", 3), (tfea, "t_net_fea", 64)):
+        if not on:
+            continue
+        conv(f"{name}.conv1", 64, k, (1,))
+        conv(f"{name}.conv2", 128, 64, (1,))
+        conv(f"{name}.conv3", 1024, 128, (1,))
+        conv(f"{name}.fc1", 512, 1024, ())
+        conv(f"{name}.fc2", 256, 512, ())
+        conv(f"{name}.fc3", k * k, 256, ())
+        for i, n in enumerate((64, 128, 1024, 512, 256), start=1):
+            sd[f"{name}.bn{i}.weight"] = rs.uniform(0.5, 1.5, n).astype(np.float32)
+            sd[f"{name}.bn{i}.bias"] = rs.normal(0, 0.1, n).astype(np.float32)
+            sd[f"{name}.bn{i}.running_mean"] = rs.normal(0, 0.2, n).astype(np.float32)
+            sd[f"{name}.bn{i}.running_var"] = rs.uniform(0.5, 1.5, n).astype(np.float32)
+    return sd

@@ -144,19 +144,42 @@ def quat2mat(q):
 
 
 # --------------------------------------------------------------------------------------
-# LPDNet embedding (model/lpdnet_model.py:103-137), t3d = tfea = False
+# LPDNet embedding (model/lpdnet_model.py:103-137) and its optional TranformNets (:19-70)
 # --------------------------------------------------------------------------------------
 
+def transform_net_forward(p, x, prefix, k):
+    """TranformNet.forward (model/lpdnet_model.py:44-70), eval mode.  x [B,k,N] -> [B,k,k].
+    The activations are F.relu (the module's LeakyReLU member is never called)."""
+    h = _f32(x)
+    for i in (1, 2, 3):                                                                 # :54-56
+        h = np.maximum(batch_norm_eval(conv1x1(h, p[prefix + f"conv{i}.weight"], p[prefix + f"conv{i}.bias"]),
+                                       p, prefix + f"bn{i}"), 0)
+    h = h.max(axis=2)                                                                   # :57-58 [B,1024]
+    for i, bn in ((1, 4), (2, 5)):                                                      # :60-61
+        h = np.maximum(batch_norm_eval(linear(h, p[prefix + f"fc{i}.weight"], p[prefix + f"fc{i}.bias"]),
+                                       p, prefix + f"bn{bn}"), 0)
+    h = linear(h, p[prefix + "fc3.weight"], p[prefix + "fc3.bias"])                     # :62
+    h = h + np.eye(k, dtype=F32).reshape(1, k * k)                                      # :66-68
+    return _f32(h.reshape(-1, k, k))
+
+
 def lpdnet_forward(p, x, slope=0.0, prefix="emb_nn.", k=20, idx_feat=None, idx_xyz=None,
-                   return_stages=False):
+                   return_stages=False, t3d=False, tfea=False):
     """x [B,3,N] -> [B,emb_dims,N].  ``idx_feat`` / ``idx_xyz`` inject neighbour sets
     (the reference allows this through get_graph_feature(x, idx=...), util/util.py:176)."""
     x = _f32(x)
     B, _, N = x.shape
     x_init = x
     g = lambda name: p[prefix + name]
+    trans = trans_feat = None
+    if t3d:                                                                             # :107-109
+        trans = transform_net_forward(p, x, prefix + "t_net3d.", 3)
+        x = _f32(np.matmul(x.transpose(0, 2, 1), trans).transpose(0, 2, 1))
     h = leaky_relu(conv1x1(x, g("conv1_lpd.weight"), g("conv1_lpd.bias")), slope)       # :111
     h = leaky_relu(conv1x1(h, g("conv2_lpd.weight"), g("conv2_lpd.bias")), slope)       # :112
+    if tfea:                                                                            # :114-118
+        trans_feat = transform_net_forward(p, h, prefix + "t_net_fea.", 64)
+        h = _f32(np.matmul(h.transpose(0, 2, 1), trans_feat).transpose(0, 2, 1))
     f64 = h
     if idx_feat is None:
         idx_feat = knn(h, k)                                                            # :122
@@ -174,7 +197,7 @@ def lpdnet_forward(p, x, slope=0.0, prefix="emb_nn.", k=20, idx_feat=None, idx_x
     out = leaky_relu(conv1x1(cat, g("conv3_lpd.weight"), g("conv3_lpd.bias")), slope)   # :135
     if return_stages:
         return out, {"f64": f64, "idx_feat": idx_feat, "idx_xyz": idx_xyz,
-                     "x1": x1, "x2": x2, "x3": x3}
+                     "x1": x1, "x2": x2, "x3": x3, "trans": trans, "trans_feat": trans_feat}
     return out
 
 

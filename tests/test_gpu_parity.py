@@ -532,6 +532,40 @@ def test_dgcnn_pointnet_vs_golden(precision):
         net.train()(x)                                             # batch-statistics BatchNorm is not implemented
 
 
+def test_lpdnet_transform_nets_vs_golden(precision):
+    """--t3d / --tfea TranformNets (model/lpdnet_model.py:19-70, 107-118), eval mode."""
+    from vcr_net_b200.model.lpdnet_model import LPDNet
+    g = load_golden("tnet")
+    x = cu(g["x"])
+    for name, t3d, tfea in (("both", True, True), ("t3d", True, False)):
+        net = LPDNet(default_args(t3d=t3d, tfea=tfea, emb_dims=128)).to(DEV).eval()
+        net.load_state_dict(synth.checkpoint_to_torch(synth.make_tnet_lpdnet_weights(21, t3d, tfea, 128)), strict=False)
+        with torch.no_grad():
+            assert rel_err(nump(net.t_net3d(x)), g[f"{name}.trans"]) < TOL
+            st = {}
+            tok = net.forward_tokens(x, idx_feat=cu(g[f"{name}.idx_feat"], torch.int32),
+                                     idx_xyz=cu(g["idx_xyz"], torch.int32), stages=st)
+            if tfea:
+                assert rel_err(nump(st["trans_feat"]), g[f"{name}.trans_feat"]) < TOL
+            assert rel_err(nump(tok).transpose(0, 2, 1), g[f"{name}.out"]) < TOL
+            out = net(x)                                                # free-running kNN
+            assert tuple(out.shape) == (2, 128, 256)
+            assert rel_err(nump(out), g[f"{name}.out"]) < 5e-4
+            assert torch.equal(st["idx_xyz"], cu(g["idx_xyz"], torch.int32))
+            with pytest.raises(RuntimeError):
+                net.train()(x)                                         # batch-statistics BatchNorm1d is not implemented
+            net.eval()
+    # a 1024-point cloud exercises the two-level cloud max and the oracle on a second size
+    p = synth.make_tnet_lpdnet_weights(21, True, True, 128)
+    x2 = synth.make_pairs(3, 1000, first_item=150)["tgt"]
+    net = LPDNet(default_args(t3d=True, tfea=True, emb_dims=128)).to(DEV).eval()
+    net.load_state_dict(synth.checkpoint_to_torch(p), strict=False)
+    want, wst = O.lpdnet_forward(p, x2, prefix="", t3d=True, tfea=True, return_stages=True)
+    with torch.no_grad():
+        tok = net.forward_tokens(cu(x2), idx_feat=cu(wst["idx_feat"], torch.int32), idx_xyz=cu(wst["idx_xyz"], torch.int32))
+    assert rel_err(nump(tok).transpose(0, 2, 1), want) < TOL
+
+
 def test_vcp_att_dist_heads_vs_golden(precision):
     g = load_golden("variants")
     args = default_args(emb_dims=64, vcp_nn="att")

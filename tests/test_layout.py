@@ -70,6 +70,19 @@ def test_state_dict_layout_and_t7_roundtrip(tmp_path, ckpt):
     assert lpdm.emb_nn.negative_slope == 0.2 and net.emb_nn.negative_slope == 0.0
 
 
+def test_lpdnet_transform_net_state_dict_layout():
+    """--t3d / --tfea: key order of the live reference's LPDNet(t3d, tfea).state_dict() (tests/golden/tnet.npz)."""
+    from vcr_net_b200.model.lpdnet_model import LPDNet
+    from oracle import synth
+    from oracle.ref_harness import default_args
+    g = load_golden("tnet")
+    for name, t3d, tfea in (("both", True, True), ("t3d", True, False)):
+        net = LPDNet(default_args(t3d=t3d, tfea=tfea, emb_dims=128))
+        assert list(net.state_dict().keys()) == [str(k) for k in g[f"{name}.keys"]]
+        res = net.load_state_dict(synth.checkpoint_to_torch(synth.make_tnet_lpdnet_weights(21, t3d, tfea, 128)), strict=False)
+        assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys)
+
+
 def test_host_svd_matches_numpy():
     from vcr_net_b200._lib import lib
     L = lib()

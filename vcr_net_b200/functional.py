@@ -75,7 +75,8 @@ def lpdnet_weights(m):
 
 
 def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None):
-    """xyz [B,3,N] -> embedding tokens [B,N,emb_dims]  (model/lpdnet_model.py:103-137, t3d=tfea=False).
+    """xyz [B,3,N] -> embedding tokens [B,N,emb_dims]  (model/lpdnet_model.py:103-137, incl. the optional t3d / tfea
+    TranformNets, eval mode).
 
     idx_feat / idx_xyz (int32 [B,N,20]) inject neighbour sets, as get_graph_feature(x, idx=...) allows."""
     W = lpdnet_weights(m)
@@ -83,8 +84,18 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
     k = m.k
     B, _, N = xyz.shape
     xyz = xyz.contiguous()
-    h1 = ops.conv3_act(xyz, W["w1"], W["b1"], slope)                         # :111
+    xyz_in = xyz
+    if m.t3d:                                                                # :107-109  x <- (x^T trans)^T = trans^T x
+        trans = transform_net_matrix(m.t_net3d, xyz)
+        xyz_in = ops.rigid_apply(xyz, trans.transpose(1, 2).contiguous(),
+                                 torch.zeros((B, 3), dtype=_F32, device=xyz.device))
+    h1 = ops.conv3_act(xyz_in, W["w1"], W["b1"], slope)                      # :111
     h2 = ops.gemm(h1, W["w2"], W["b2"], act=1, slope=slope)                  # :112  [B,N,64]
+    if m.tfea:                                                               # :114-118  per-cloud [N,64] x [64,64]
+        trans_feat = transform_net_matrix(m.t_net_fea, h2)
+        h2t = torch.empty_like(h2)
+        ops.bgemm(h2, 64, N * 64, 0, trans_feat, 64, 64 * 64, 0, 1, h2t, 64, N * 64, 0, N, 64, 64, B, 1)
+        h2 = h2t
     if idx_feat is None:
         idx_feat = ops.knn_topk(h2, k, token_major=True)                     # :122 (feature-space kNN)
     tc = config.precision != "fp32"
@@ -119,7 +130,61 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
                     slope=slope, c=emb)
     if stages is not None:
         stages.update(f64=h2, idx_feat=idx_feat, idx_xyz=idx_xyz, cat=cat, h1=h1, pq1=pq1, pq3=pq3)
+        if m.t3d:
+            stages.update(trans=trans)
+        if m.tfea:
+            stages.update(trans_feat=trans_feat)
     return emb
+
+
+# --------------------------------------------------------------------------------------------------
+# TranformNet (model/lpdnet_model.py:19-70): the --t3d / --tfea input / feature alignment matrices
+# --------------------------------------------------------------------------------------------------
+
+def _fold_bn_bias(layer, bn):
+    """Eval-mode BatchNorm1d folded into the biased conv / linear in front of it."""
+    w = layer.weight.detach().reshape(layer.weight.shape[0], -1)
+    s = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    return (w * s[:, None]).contiguous(), ((layer.bias.detach() - bn.running_mean.detach()) * s + bn.bias.detach()).contiguous()
+
+
+def cloud_max(h: torch.Tensor, B: int, N: int):
+    """h [B*N, C] -> [B, C]: max over the points of each cloud (torch.max(x, 2), :57), as a tree of vcr_edge_max passes
+    (<= 32 rows per thread and pass) so a 1024-point cloud is not reduced by one serial loop."""
+    C = h.shape[1]
+    n = N
+    while n > 1:
+        k = next((d for d in range(min(32, n), 1, -1) if n % d == 0), n)
+        out = torch.empty((B * (n // k), C), dtype=_F32, device=h.device)
+        ops.edge_max(h, k, out)
+        h, n = out, n // k
+    return h
+
+
+def transform_net_matrix(tn, x: torch.Tensor):
+    """TranformNet.forward.  x = xyz [B,3,N] (k = 3) or feature tokens [B,N,64] (k = 64)  ->  [B,k,k].
+    conv1-3 + BN + ReLU per point (GEMMs), max over the cloud, fc1-2 + BN + ReLU, fc3 + identity."""
+    _require_eval(tn)
+    mode = config.precision
+    k = tn.k
+    layers = [(tn.conv1, tn.bn1), (tn.conv2, tn.bn2), (tn.conv3, tn.bn3), (tn.fc1, tn.bn4), (tn.fc2, tn.bn5)]
+    params = [p for l, bn in layers for p in (l.weight, l.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+    W = packed(tn, "tnet", params, lambda: [_fold_bn_bias(l, bn) for l, bn in layers])
+    if k == 3:
+        B, _, N = x.shape
+        h = ops.conv3_act(x.contiguous(), W[0][0], W[0][1], 0.0).view(B * N, 64)          # :54
+    else:
+        B, N, _ = x.shape
+        h = ops.gemm(x.reshape(B * N, k), W[0][0], W[0][1], act=1, slope=0.0)
+    h, hop = _edge_mlp(h, *W[1], mode, True)                                              # :55  [B*N,128]
+    h, _ = _edge_mlp(hop if hop is not None else h, *W[2], mode, False)                   # :56  [B*N,1024]
+    g = cloud_max(h, B, N)                                                                # :57-58 [B,1024]
+    g = ops.gemm(g, W[3][0], W[3][1], act=1, slope=0.0)                                   # :60
+    g = ops.gemm(g, W[4][0], W[4][1], act=1, slope=0.0)                                   # :61
+    iden = torch.eye(k, dtype=_F32, device=g.device).reshape(1, k * k).repeat(B, 1)      # :64-66
+    w3 = tn.fc3.weight.detach().contiguous()
+    out = ops.gemm(g, w3, tn.fc3.bias.detach().contiguous(), residual=iden)               # :62, :68
+    return out.view(B, k, k)
 
 
 class LPDNetTrainFn(torch.autograd.Function):

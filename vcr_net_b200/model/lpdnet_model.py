@@ -13,6 +13,34 @@ from .. import functional as Fn
 from .. import ops
 
 
+class TranformNet(nn.Module):
+    """model/lpdnet_model.py:19-70 (the reference's spelling).  forward(x [B,k,N]) -> [B,k,k]; eval mode only
+    (BatchNorm1d running statistics folded into the convs / linears)."""
+
+    def __init__(self, k=3, negative_slope=1e-2):
+        super().__init__()
+        self.negative_slope = negative_slope
+        self.conv1 = nn.Conv1d(k, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 1024, 1)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, k * k)
+        self.relu = nn.LeakyReLU(negative_slope=self.negative_slope)      # never called by the reference's forward
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.bn4 = nn.BatchNorm1d(512)
+        self.bn5 = nn.BatchNorm1d(256)
+        self.k = k
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self.k == 3:
+            return Fn.transform_net_matrix(self, x)
+        return Fn.transform_net_matrix(self, ops.transpose_batched(x.contiguous()))
+
+
 class LPDNet(nn.Module):
     """model/lpdnet_model.py:73-137.  forward(x [B,3,N]) -> [B,emb_dims,N]."""
 
@@ -23,8 +51,6 @@ class LPDNet(nn.Module):
         self.t3d = args.t3d
         self.tfea = args.tfea
         self.emb_dims = args.emb_dims
-        if self.t3d or self.tfea:
-            raise Exception("Not implemented: TranformNet (t3d/tfea) is outside the accelerated path")
         act = lambda: nn.LeakyReLU(negative_slope=self.negative_slope)
         self.convDG1 = nn.Sequential(nn.Conv2d(64 * 2, 128, kernel_size=1, bias=True), act())
         self.convDG2 = nn.Sequential(nn.Conv2d(128, 128, kernel_size=1, bias=True), act())
@@ -32,10 +58,16 @@ class LPDNet(nn.Module):
         self.conv1_lpd = nn.Conv1d(3, 64, kernel_size=1, bias=True)
         self.conv2_lpd = nn.Conv1d(64, 64, kernel_size=1, bias=True)
         self.conv3_lpd = nn.Conv1d(512, self.emb_dims, kernel_size=1, bias=True)
+        if self.t3d:
+            self.t_net3d = TranformNet(3)
+        if self.tfea:
+            self.t_net_fea = TranformNet(64)
 
     def forward_tokens(self, x, idx_feat=None, idx_xyz=None, stages=None):
         """x [B,3,N] -> tokens [B,N,emb_dims] (internal fast path, no output transpose)."""
         if stages is None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.t3d or self.tfea:
+                raise Exception("Not implemented: backward through TranformNet (t3d/tfea); run under torch.no_grad()")
             return Fn.lpdnet_tokens_train(self, x, idx_feat=idx_feat, idx_xyz=idx_xyz)     # training: custom backward
         return Fn.lpdnet_tokens(self, x, idx_feat=idx_feat, idx_xyz=idx_xyz, stages=stages)
 
