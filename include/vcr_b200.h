@@ -45,6 +45,16 @@ size_t vcr_knn_workspace_bytes(int B, int N);
 int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
                  int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Tensor-core variant of the same function for feature-space kNN (16 <= D <= 128, k <= 30, token-major only):
+ * tcgen05 distance tiles from the operand-format copy of x ([2 planes][B*N][ld] fp16 hi / lo*2^11, vcr_to_operand)
+ * prefilter ranks 0..k+8, the survivors are re-ranked with the canonical fp32 chain and certified per query
+ * (error bound eps on the approximate distances); uncertified 32-query groups are recomputed by the exact kernel in
+ * the same launch sequence.  Output bit-identical to vcr_knn_topk on every input.  The last 4 bytes of the workspace
+ * hold the number of queries that needed the exact kernel (telemetry). */
+size_t vcr_knn_tc_workspace_bytes(int B, int N);
+int vcr_knn_topk_tc(const float* x, const void* xop, int ld, long long plane_stride, int B, int D, int N, int k,
+                    int32_t* idx32, int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- get_graph_feature: util/util.py:176-199 ---------------------------------------------------
  * xt token-major [B,N,D]; idx [B,N,k]; out [B,2D,N,k] contiguous = concat(x[idx], x centre). */
 int vcr_graph_feature(const float* xt, int B, int D, int N, int k, const int* idx, float* out,

@@ -25,3 +25,15 @@ for (B, D, N, tm) in [(32, 64, 1024, True), (32, 3, 1024, False), (48, 64, 768, 
     xc = (x[:nb].transpose(1, 2) if tm else x[:nb]).contiguous().cpu().numpy()
     ok = np.array_equal(idx[:nb].cpu().numpy(), canon.knn(xc, 20)) if N <= 4096 else None
     print(f"B={B} D={D} N={N} tm={tm}: {ms*1e3:8.1f} us  {fl/ms/1e9:6.2f} TFLOP/s ({fl/ms/1e9/FP32_PEAK*100:4.1f}% of {FP32_PEAK:.1f} fp32 FMA peak)  exact={ok}")
+    if tm and ops.knn_tc_supported(D, 20):
+        xop = ops.to_operand(x.view(B * N, D), "h3")
+        for _ in range(3):
+            idx2, fl_q = ops.knn_topk_tc(x, xop, 20, want_flagged=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            idx2 = ops.knn_topk_tc(x, xop, 20)
+        e1.record(); torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 10
+        print(f"    tcgen05 prefilter + exact re-rank: {ms2*1e3:8.1f} us ({ms/ms2:4.2f}x)  identical={bool(torch.equal(idx, idx2))}  "
+              f"queries through the exact kernel: {int(fl_q.item())} of {B*N}")

@@ -85,6 +85,67 @@ def test_knn_shapes(D, N, k, tm):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("D,N,k", [(64, 130, 20), (64, 1024, 20), (64, 768, 20), (64, 2048, 20), (128, 515, 20),
+                                   (16, 300, 5), (96, 257, 30), (32, 21, 20), (64, 4096, 20), (128, 1000, 1)])
+def test_knn_tc_prefilter_bit_exact(D, N, k):
+    """tcgen05 prefilter + exact re-rank == canonical C oracle, bit for bit; on generic data almost nothing needs the
+    exact kernel."""
+    rs = np.random.RandomState(N + D + k)
+    x = rs.randn(3, D, N).astype(np.float32)
+    want = canon.knn(x, k)
+    xt = cu(np.ascontiguousarray(x.transpose(0, 2, 1)))
+    got, flagged = ops.knn_topk_tc(xt, None, k, want_flagged=True)
+    assert np.array_equal(nump(got), want)
+    assert int(flagged.item()) <= 0.02 * 3 * N, int(flagged.item())
+    got32, got64 = ops.knn_topk_tc(xt, ops.to_operand(xt.view(3 * N, D), "h3"), k, want64=True)
+    assert np.array_equal(nump(got64), want) and got64.dtype == torch.int64 and torch.equal(got32.long(), got64)
+
+
+def test_knn_tc_prefilter_adversarial_inputs():
+    """Inputs that defeat the certificate (exact ties, duplicates, cancellation, out-of-range magnitudes) fall back to the
+    exact kernel inside the same call: still bit-exact."""
+    rs = np.random.RandomState(17)
+    g = load_golden("knn")
+    cases = {
+        "grid_ties": g["x64g"],                                                         # dyadic grid: real ties
+        "real_features": g["x64f"],                                                     # LPDNet conv2 output
+        "duplicates": np.repeat(rs.randn(2, 64, 100).astype(np.float32), 4, axis=2),    # every point 4 times
+        "zeros": np.zeros((1, 64, 200), np.float32),
+        "dead_half": np.concatenate([np.zeros((2, 64, 300), np.float32), rs.randn(2, 64, 300).astype(np.float32)], 2),
+        "offset": (rs.randn(2, 64, 500) * 0.01 + 100.0).astype(np.float32),             # cancellation: eps >> gaps
+        "huge": (rs.randn(2, 64, 300) * 1e6).astype(np.float32),                        # outside the fp16 split range
+        "tiny": (rs.randn(2, 64, 300) * 1e-6).astype(np.float32),
+        "mixed_scale": (rs.randn(2, 64, 400) * np.exp(rs.randn(2, 1, 400) * 2)).astype(np.float32),
+    }
+    n_flag = {}
+    for name, x in cases.items():
+        xt = cu(np.ascontiguousarray(x.transpose(0, 2, 1)))
+        got, flagged = ops.knn_topk_tc(xt, None, 20, want_flagged=True)
+        assert np.array_equal(nump(got), canon.knn(x, 20)), name
+        n_flag[name] = int(flagged.item())
+    assert n_flag["real_features"] <= 0.05 * g["x64f"].shape[0] * g["x64f"].shape[2], n_flag
+    assert n_flag["zeros"] == 200 and n_flag["huge"] == 600 and n_flag["tiny"] == 600, n_flag
+    assert n_flag["offset"] > 0, n_flag
+
+
+def test_knn_tc_matches_simt_inside_lpdnet(net_whole):
+    """The LPDNet feature-space neighbour sets are identical with the prefilter on and off (h3 mode)."""
+    from vcr_net_b200 import config
+    x = cu(synth.make_pairs(4, 1024, first_item=33)["src"])
+    old_p, old_k = config.precision, config.knn_tc
+    try:
+        config.set_precision("h3")
+        st_on, st_off = {}, {}
+        config.knn_tc = "1"
+        a = net_whole.emb_nn.forward_tokens(x, stages=st_on)
+        config.knn_tc = "0"
+        b = net_whole.emb_nn.forward_tokens(x, stages=st_off)
+        assert torch.equal(st_on["idx_feat"], st_off["idx_feat"]) and torch.equal(a, b)
+    finally:
+        config.set_precision(old_p)
+        config.knn_tc = old_k
+
+
 def test_knn_duplicates_ties():
     rs = np.random.RandomState(5)
     base = synth.grid_cloud(rs, (1, 3, 64), 3, -0.5, 0.5)      # coarse grid: many exact ties / duplicates

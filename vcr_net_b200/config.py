@@ -4,7 +4,8 @@
   "h3"    tcgen05 tensor cores with 3-term fp16 split operands: fp32-level accuracy (the parity mode
           on tensor cores)
   "fp16" / "bf16"  single-pass tensor-core throughput modes (reported separately with their tolerance)
-kNN / FPS / top-K selections and the SVD head always run in exact fp32 / fp64 arithmetic.
+kNN / FPS / top-K selections and the SVD head always return the exact fp32 / fp64 result (the tensor-core kNN
+prefilter only narrows the candidates; the kept neighbours are re-ranked with the canonical fp32 chain).
 """
 import os
 
@@ -16,6 +17,20 @@ flash_attention = os.environ.get("VCR_FLASH", "1") != "0"
 # (bit-identical outputs).  Off by default so the default path does exactly the work the reference does per iteration;
 # bench.py reports the throughput with the switch on as a separate, labelled field.
 reuse_target_embedding = os.environ.get("VCR_REUSE_TGT_EMB", "0") == "1"
+
+
+# feature-space kNN (16 <= D <= 128): tcgen05 prefilter + exact re-rank (csrc/knn.cu, bit-identical indices).
+# Measured on B200 (scripts/knn_bench.py, D = 64): 0.73x of the FP32 SIMT kernel at N = 1024 (its 128-candidate tiles cost
+# more sort / merge rounds than the SIMT kernel's 512-candidate tiles save in FMAs), 1.07x at N = 4096, 1.30x at
+# N = 16384.  "auto" (default) therefore uses it from N >= 4096 in the tensor-core precision modes; "1" always, "0" never.
+knn_tc = os.environ.get("VCR_KNN_TC", "auto")
+KNN_TC_MIN_N = 4096
+
+
+def use_knn_tc(N: int) -> bool:
+    if precision == "fp32" or knn_tc in ("0", False):
+        return False
+    return True if knn_tc in ("1", True) else N >= KNN_TC_MIN_N
 
 
 def set_precision(p: str):

@@ -21,7 +21,7 @@
 // Roofline: bytes = 4*D*N in + 4*k*N out per cloud (candidate chunks are re-read from L2 by the N/32
 // CTAs of a cloud), flops = 2*D*N^2 (+ ~N^2 select steps): FP32-FMA bound at D = 64, selection
 // (issue) bound at D = 3 -- DESIGN.md section 4.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -112,38 +112,39 @@ __device__ __forceinline__ void merge32_desc(Key (&run)[W], const Key (&add)[W],
     }
 }
 
-// Filter W queries' chunk rows by their thresholds into buf (capacity TC keys), then sort the survivors 32 at a
-// time and merge them into the running lists.  Returns false, leaving `run` untouched, if buf would overflow
-// (impossible for W == 1).
-template <int W>
-__device__ __forceinline__ bool filter_merge(const float* drows, const float (&tau)[W], Key (&run)[W], uint2* buf,
-                                             int j0, int lane) {
+// Filter W queries' chunk rows (TCN candidates each, row stride LDD floats) by their thresholds into buf (capacity
+// CAP keys), then sort the survivors 32 at a time and merge them into the running lists.  Returns false, leaving
+// `run` untouched, if buf would overflow (impossible for W == 1 when CAP >= TCN).
+template <int W, int TCN, int LDD, int CAP>
+__device__ __forceinline__ bool filter_merge_t(const float* drows, const float (&tau)[W], Key (&run)[W], uint2* buf,
+                                               int j0, int lane) {
+    constexpr int RP = TCN / 32;
     const uint32_t lt = (1u << lane) - 1u;
     int cnt[W], off[W];
     int base = 0;
     __syncwarp();
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-        const float* dr = drows + w * TC + lane;
-        float v[RPL];
+        const float* dr = drows + w * LDD + lane;
+        float v[RP];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) v[r] = dr[r * 32];
+        for (int r = 0; r < RP; ++r) v[r] = dr[r * 32];
         off[w] = base;
         int n = base;
-        // branch-free: the 16 ballots are independent, only the running offset chains
+        // branch-free: the ballots are independent, only the running offset chains
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
+        for (int r = 0; r < RP; ++r) {
             const bool p = v[r] >= tau[w];
             const uint32_t bal = __ballot_sync(0xffffffffu, p);
             const int pos = n + __popc(bal & lt);
-            if (p && pos < TC) buf[pos] = make_uint2(~(uint32_t)(j0 + r * 32 + lane), okey(v[r]));
+            if (p && pos < CAP) buf[pos] = make_uint2(~(uint32_t)(j0 + r * 32 + lane), okey(v[r]));
             n += __popc(bal);
         }
         cnt[w] = n - base;
         base = n;
     }
     __syncwarp();
-    if (base > TC) return false;
+    if (base > CAP) return false;
     int rounds = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) rounds = max(rounds, (cnt[w] + 31) >> 5);
@@ -159,6 +160,11 @@ __device__ __forceinline__ bool filter_merge(const float* drows, const float (&t
         merge32_desc<W>(run, e, lane);
     }
     return true;
+}
+template <int W>
+__device__ __forceinline__ bool filter_merge(const float* drows, const float (&tau)[W], Key (&run)[W], uint2* buf,
+                                             int j0, int lane) {
+    return filter_merge_t<W, TC, TC, TC>(drows, tau, run, buf, j0, lane);
 }
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
@@ -182,7 +188,9 @@ struct Smem {
 template <int DCH, bool TOKEN_MAJOR>
 __global__ void __launch_bounds__(NT, 2)
 knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int D, int N, int k,
-                  int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+                  int32_t* __restrict__ idx32, int64_t* __restrict__ idx64, const int* __restrict__ redo) {
+    // redo != null: this launch only repairs the 32-query groups the tensor-core kernel could not certify
+    if (redo != nullptr && redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
     using S = Smem<DCH>;
     constexpr int DCP = S::DCP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -346,7 +354,7 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
 
 template <int DCH, bool TM>
 int launch_knn(const float* x, const float* xx, int B, int D, int N, int k, int32_t* i32, int64_t* i64,
-               cudaStream_t st) {
+               cudaStream_t st, const int* redo = nullptr) {
     auto kern = knn_select_kernel<DCH, TM>;
     const size_t smem = Smem<DCH>::total;
     static bool configured = false;     // idempotent attribute, benign race
@@ -356,10 +364,298 @@ int launch_knn(const float* x, const float* xx, int B, int D, int N, int k, int3
         configured = true;
     }
     dim3 grid(vcr_cdiv(N, TQ), B);
-    kern<<<grid, NT, smem, st>>>(x, xx, D, N, k, i32, i64);
+    kern<<<grid, NT, smem, st>>>(x, xx, D, N, k, i32, i64, redo);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
+
+// =====================================================================================================
+// Tensor-core variant for feature-space kNN (16 <= D <= 128, token-major): tcgen05 distance tiles as a
+// PREFILTER, exact canonical re-rank, certified per query.
+//
+//   approx  dot~_ij from the 3-term fp16 split of the operand-format copy of x (hi*hi' in one TMEM accumulator,
+//           hi*lo' + lo*hi' in a second, combined in fp32), pd~ = (-xx_j - (-2 dot~)) - xx_i with the CANONICAL xx.
+//           A CTA owns 128 queries (UMMA M) and walks the cloud 128 candidates at a time (UMMA N): one TMA
+//           producer / MMA issuer warp, 16 consumer warps that read the 128 x 128 tile from TMEM, write pd~ to a
+//           padded smem tile and run the same warp-per-query threshold filter + shuffle-bitonic merge as the exact
+//           kernel, but keeping ranks 0..ksel (ksel = k + 8) of pd~ instead of 0..k.  MMA of chunk c+1 overlaps
+//           the selection of chunk c.
+//   exact   the 32 list entries of a query are re-evaluated with the canonical fp32 fma chain (one entry per lane)
+//           and sorted by (pd, lower index): ranks 1..k are the answer IF no candidate outside the certified part
+//           of the list can reach rank k:   pd_exact(rank k) > pd~(rank ksel) + eps,   eps >= |pd~ - pd| for this
+//           query against any candidate (bound below).  Otherwise the query's 32-group is flagged and recomputed
+//           by the exact kernel (same launch sequence, no host sync).  The result is therefore bit-identical to
+//           vcr_knn_topk on every input; only the speed depends on the data.
+//   eps     |dot~ - dot_canon| <= (split 3*2^-22 + fp32 chain D*2^-24 + TMEM accumulation D*2^-24) |x_i||x_j|
+//           < 2^-15 |x_i||x_j| for D <= 128; pd doubles it and adds <= 2 ulp of (xx_i + xx_j + 2|dot|):
+//           eps_i = 2^-14 sqrt(xx_i * xxmax) + 2^-20 xxmax, xxmax = max_j xx_j of the cloud.
+//           Clouds with xxmax outside [2^-20, 2^30] (fp16 range of the split) go to the exact kernel entirely.
+// =====================================================================================================
+constexpr int T2Q = 128;                  // queries per CTA
+constexpr int T2C = 128;                  // candidates per chunk
+constexpr int T2LD = T2C + 1;             // padded row stride of the distance tile (conflict-free row-per-thread stores)
+constexpr int T2CAP = 192;                // survivor keys per consumer warp
+constexpr int T2CW = 16;                  // consumer warps
+constexpr int T2NT = (T2CW + 1) * 32;     // + 1 producer warp
+constexpr int T2TILE = 128 * 128;         // bytes of one [128 rows][64 x fp16] swizzled tile
+constexpr int T2QW = 4;                   // queries per selection pass (2 passes per warp)
+
+struct KnnTcParams {
+    const float* x;          // [B, N, D] fp32 token-major
+    const float* xx;         // [B*N] canonical squared norms
+    const uint32_t* xxmax;   // [B] bit pattern of max_j xx_j
+    int* redo;               // [B * ceil(N/32)] flags for the exact kernel
+    int* nflag;              // [1] number of uncertified queries (telemetry)
+    int D, N, k, ksel, KB;
+    int32_t* idx32;
+    int64_t* idx64;
+};
+
+__host__ __device__ constexpr size_t knn_tc_smem_bytes(int KB) {
+    return (size_t)2 * KB * 2 * T2TILE + (size_t)T2Q * T2LD * 4 + (size_t)T2CW * T2CAP * 8 + 2 * T2C * 4 + 128 + 1024;
+}
+
+__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(T2CW * 32) : "memory"); }
+
+// one selection pass: 4 queries of this warp against the current 128-candidate tile
+__device__ __forceinline__ void select_pass_tc(const float* drows, Key (&run)[T2QW], uint2* buf, int j0, int ksel,
+                                               int lane, bool first) {
+    float tau[T2QW];
+    if (first) {
+        float m[T2QW];
+#pragma unroll
+        for (int w = 0; w < T2QW; ++w) {
+            const float* dr = drows + w * T2LD + lane;
+            float mm = dr[0];
+#pragma unroll
+            for (int r = 1; r < T2C / 32; ++r) mm = fmaxf(mm, dr[r * 32]);
+            m[w] = mm;
+        }
+        sort32_desc_f<T2QW>(m, lane);
+#pragma unroll
+        for (int w = 0; w < T2QW; ++w) tau[w] = __shfl_sync(0xffffffffu, m[w], ksel);
+    } else {
+#pragma unroll
+        for (int w = 0; w < T2QW; ++w) tau[w] = okey_inv(__shfl_sync(0xffffffffu, run[w].hi, ksel));
+    }
+    if (!filter_merge_t<T2QW, T2C, T2LD, T2CAP>(drows, tau, run, buf, j0, lane)) {
+#pragma unroll
+        for (int w = 0; w < T2QW; ++w) {
+            float t1[1] = {tau[w]};
+            Key r1[1] = {run[w]};
+            filter_merge_t<1, T2C, T2LD, T2CAP>(drows + w * T2LD, t1, r1, buf, j0, lane);
+            run[w] = r1[0];
+        }
+    }
+}
+
+__global__ void knn_sqnorm_max_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ xx,
+                                      uint32_t* __restrict__ xxmax) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bits = 0u;
+    if (i < N) {
+        const float* r = x + ((size_t)b * N + i) * D;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(r[d], r[d], acc);      // canonical chain (oracle/canon.c)
+        xx[(size_t)b * N + i] = acc;
+        bits = __float_as_uint(acc);                                   // acc >= 0 (or NaN, which sorts above +inf)
+    }
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(xxmax + b, bits);
+}
+
+__global__ void __launch_bounds__(T2NT, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const KnnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int KB = p.KB, N = p.N, D = p.D, k = p.k, ksel = p.ksel;
+    const int opb = KB * 2 * T2TILE;                                   // bytes of one operand block (all k-blocks, hi+lo)
+    uint8_t* q_s = smem;
+    uint8_t* c_s = smem + opb;
+    float* dist = reinterpret_cast<float*>(smem + 2 * opb);            // [128][129]
+    uint2* surv = reinterpret_cast<uint2*>(dist + T2Q * T2LD);         // [16][192]
+    float* xxc_s = reinterpret_cast<float*>(surv + T2CW * T2CAP);      // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xxc_s + 2 * T2C);
+    uint64_t* q_full = bars + 0;
+    uint64_t* c_full = bars + 1;
+    uint64_t* mma_done = bars + 2;
+    uint64_t* tmem_empty = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * T2Q;
+    const int nq32 = (N + 31) / 32;
+    const float* xxb = p.xx + (size_t)b * N;
+    const int nch = (N + T2C - 1) / T2C;
+
+    if (warp == T2CW && lane == 0) {
+        tc::tma_prefetch_desc(&tmX);
+        tc::mbar_init(q_full, 1); tc::mbar_init(c_full, 1); tc::mbar_init(mma_done, 1); tc::mbar_init(tmem_empty, T2CW);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(tmem_slot, 256); tc::tmem_relinquish(); }
+    if (tid < T2C) xxc_s[tid] = tid < N ? xxb[tid] : 0.f;
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const float xm = __uint_as_float(p.xxmax[b]);
+    const bool cloud_ok = xm >= 9.5367431640625e-07f && xm <= 1073741824.f;     // [2^-20, 2^30]; false for NaN
+    if (!cloud_ok) {
+        // outside the fp16 range of the split: every 32-group of this CTA goes to the exact kernel
+        if (tid < T2Q / 32 && q0 + tid * 32 < N) {
+            p.redo[b * nq32 + q0 / 32 + tid] = 1;
+            atomicAdd(p.nflag, min(32, N - (q0 + tid * 32)));
+        }
+    } else if (warp == T2CW) {
+        // ============================== TMA producer + MMA issuer ==============================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc(T2Q, T2C, 0);
+            const int row0 = b * N;
+            tc::mbar_expect_tx(q_full, opb);
+            for (int kb = 0; kb < KB; ++kb)
+                for (int pl = 0; pl < 2; ++pl)
+                    tc::tma_load_3d(q_s + (kb * 2 + pl) * T2TILE, &tmX, q_full, kb * 64, row0 + q0, pl);
+            tc::mbar_expect_tx(c_full, opb);
+            for (int kb = 0; kb < KB; ++kb)
+                for (int pl = 0; pl < 2; ++pl)
+                    tc::tma_load_3d(c_s + (kb * 2 + pl) * T2TILE, &tmX, c_full, kb * 64, row0, pl);
+            tc::mbar_wait(q_full, 0);
+            const uint32_t q_addr = tc::smem_u32(q_s), c_addr = tc::smem_u32(c_s);
+            const uint32_t d0 = tmem_base, d1 = tmem_base + T2C;
+            for (int c = 0; c < nch; ++c) {
+                tc::mbar_wait(c_full, c & 1);
+                if (c > 0) tc::mbar_wait(tmem_empty, (c - 1) & 1);
+                tc::tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * 2) * T2TILE);
+                    const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * 2 + 1) * T2TILE);
+                    const uint64_t c_hi = tc::umma_desc_k_sw128(c_addr + (kb * 2) * T2TILE);
+                    const uint64_t c_lo = tc::umma_desc_k_sw128(c_addr + (kb * 2 + 1) * T2TILE);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (kb | kk) != 0;
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        tc::umma_f16(d0, q_hi + adv, c_hi + adv, idesc, acc);
+                        tc::umma_f16(d1, q_hi + adv, c_lo + adv, idesc, acc);
+                        tc::umma_f16(d1, q_lo + adv, c_hi + adv, idesc, 1);
+                    }
+                }
+                tc::umma_commit(mma_done);
+                tc::mbar_wait(mma_done, c & 1);                      // candidate tile consumed
+                if (c + 1 < nch) {
+                    tc::mbar_expect_tx(c_full, opb);
+                    for (int kb = 0; kb < KB; ++kb)
+                        for (int pl = 0; pl < 2; ++pl)
+                            tc::tma_load_3d(c_s + (kb * 2 + pl) * T2TILE, &tmX, c_full, kb * 64, row0 + (c + 1) * T2C, pl);
+                }
+            }
+        }
+    } else {
+        // ============================== consumers: TMEM -> pd~ tile -> selection ==============================
+        const int qq = warp & 3, cgp = warp >> 2;
+        const int row = qq * 32 + lane;
+        const uint32_t t_adr = tmem_base + ((uint32_t)(qq * 32) << 16) + cgp * 32;
+        const int qrow = q0 + row;
+        const float xxq_row = qrow < N ? xxb[qrow] : 0.f;
+        uint2* buf = surv + (size_t)warp * T2CAP;
+        Key runA[T2QW], runB[T2QW];
+#pragma unroll
+        for (int w = 0; w < T2QW; ++w) { runA[w].hi = runA[w].lo = 0u; runB[w].hi = runB[w].lo = 0u; }
+
+        for (int c = 0; c < nch; ++c) {
+            const int j0 = c * T2C;
+            if (tid < T2C && c + 1 < nch) {
+                const int j = j0 + T2C + tid;
+                xxc_s[((c + 1) & 1) * T2C + tid] = j < N ? xxb[j] : 0.f;
+            }
+            tc::mbar_wait(mma_done, c & 1);
+            tc::tc_fence_after();
+            float pdv[32];
+            {
+                const float* xc = xxc_s + (c & 1) * T2C + cgp * 32;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r0[16], r1[16];
+                    tc::tmem_ld_32x16(t_adr + h * 16, r0);
+                    tc::tmem_ld_32x16(t_adr + T2C + h * 16, r1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float dot = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
+                        pdv[h * 16 + i] = __fsub_rn(__fsub_rn(-xc[h * 16 + i], -2.f * dot), xxq_row);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tmem_empty);              // the MMA of chunk c+1 may overwrite TMEM
+            {
+                float* drow = dist + row * T2LD + cgp * 32;
+                const int jc = j0 + cgp * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) drow[i] = (jc + i < N) ? pdv[i] : -INFINITY;
+            }
+            cons_bar();
+            select_pass_tc(dist + (size_t)(warp * 8) * T2LD, runA, buf, j0, ksel, lane, c == 0);
+            select_pass_tc(dist + (size_t)(warp * 8 + T2QW) * T2LD, runB, buf, j0, ksel, lane, c == 0);
+            cons_bar();                                              // tile reads done before the next chunk's stores
+        }
+
+        // ---- exact re-rank + certificate, one query at a time, one list entry per lane ----
+        const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+#pragma unroll
+        for (int qi = 0; qi < 2 * T2QW; ++qi) {
+            const int q = q0 + warp * 8 + qi;
+            if (q >= N) continue;                                    // warp-uniform
+            const Key a = qi < T2QW ? runA[qi & 3] : runB[qi & 3];
+            const uint32_t thr_hi = __shfl_sync(0xffffffffu, a.hi, ksel);
+            const int j = (int)(~a.lo);
+            const bool valid = j >= 0 && j < N;
+            const float xxq = xxb[q];
+            Key e[1];
+            e[0].hi = 0u; e[0].lo = 0u;
+            if (valid) {
+                const float* xq = p.x + ((size_t)b * N + q) * D;
+                const float* xj = p.x + ((size_t)b * N + j) * D;
+                float acc = 0.f;
+                if (vec) {
+                    for (int d = 0; d < D; d += 4) {
+                        const float4 qv = __ldg(reinterpret_cast<const float4*>(xq + d));
+                        const float4 cv = __ldg(reinterpret_cast<const float4*>(xj + d));
+                        acc = fmaf(qv.x, cv.x, acc); acc = fmaf(qv.y, cv.y, acc);
+                        acc = fmaf(qv.z, cv.z, acc); acc = fmaf(qv.w, cv.w, acc);
+                    }
+                } else {
+                    for (int d = 0; d < D; ++d) acc = fmaf(__ldg(xq + d), __ldg(xj + d), acc);
+                }
+                const float pd = __fsub_rn(__fsub_rn(-xxb[j], -2.f * acc), xxq);
+                e[0].hi = okey(pd); e[0].lo = a.lo;
+            }
+            sort32_desc<1>(e, lane);
+            const uint32_t ek_hi = __shfl_sync(0xffffffffu, e[0].hi, k);
+            const float eps = 6.103515625e-05f * sqrtf(xxq * xm) + 9.5367431640625e-07f * xm;
+            const bool safe = ek_hi != 0u && (thr_hi == 0u || okey_inv(ek_hi) > okey_inv(thr_hi) + eps);
+            if (safe) {
+                if (lane >= 1 && lane <= k) {
+                    const int jn = (int)(~e[0].lo);
+                    const size_t o = ((size_t)b * N + q) * k + lane - 1;
+                    if (p.idx32) p.idx32[o] = jn;
+                    if (p.idx64) p.idx64[o] = (int64_t)jn;
+                }
+            } else if (lane == 0) {
+                p.redo[b * nq32 + q / 32] = 1;
+                atomicAdd(p.nflag, 1);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 
 }  // namespace
 
@@ -384,4 +680,44 @@ VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_m
                            : launch_knn<4, false>(x, xx, B, D, N, k, idx32, idx64, stream);
     return token_major ? launch_knn<16, true>(x, xx, B, D, N, k, idx32, idx64, stream)
                        : launch_knn<16, false>(x, xx, B, D, N, k, idx32, idx64, stream);
+}
+
+// ---- tensor-core prefilter + exact re-rank (16 <= D <= 128, token-major) --------------------------------------
+// workspace layout (4-byte words): xx [B*N] | xxmax [B] | redo [B*ceil(N/32)] | nflag [1]
+VCR_API size_t vcr_knn_tc_workspace_bytes(int B, int N) {
+    return ((size_t)B * N + (size_t)B + (size_t)B * ((N + 31) / 32) + 1) * 4;
+}
+
+// x: fp32 [B,N,D] token-major; xop: its operand-format copy [2 planes][B*N][ld] (fp16 hi, lo*2^11; vcr_to_operand).
+// Writes exactly what vcr_knn_topk writes (bit-identical indices) -- see the kernel comment for the certificate.
+// After the call, the last word of the workspace holds the number of queries that went through the exact kernel.
+VCR_API int vcr_knn_topk_tc(const float* x, const void* xop, int ld, long long plane_stride, int B, int D, int N, int k,
+                            int32_t* idx32, int64_t* idx64, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream) {
+    VCR_REQUIRE(x && xop && (idx32 || idx64) && B > 0 && N > 0 && k >= 1);
+    if (N < k + 1) return VCR_ERR_INVALID;
+    if (D < 16 || D > 128 || k > 30 || (long long)B * N > 0x7fffffffLL || B > 65535) return VCR_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vcr_knn_tc_workspace_bytes(B, N)) return VCR_ERR_WORKSPACE;
+    const int nq32 = (N + 31) / 32;
+    float* xx = reinterpret_cast<float*>(workspace);
+    uint32_t* xxmax = reinterpret_cast<uint32_t*>(xx + (size_t)B * N);
+    int* redo = reinterpret_cast<int*>(xxmax + B);
+    int* nflag = redo + (size_t)B * nq32;
+    if (cudaMemsetAsync(xxmax, 0, ((size_t)B + (size_t)B * nq32 + 1) * 4, stream) != cudaSuccess) return VCR_ERR_LAUNCH;
+    dim3 g(vcr_cdiv(N, 256), B);
+    knn_sqnorm_max_kernel<<<g, 256, 0, stream>>>(x, D, N, xx, xxmax);
+    VCR_CHECK_LAUNCH();
+    CUtensorMap tm;
+    int rc = vcr_make_operand_tmap(&tm, xop, D, (long long)B * N, ld, plane_stride, 2, T2Q);
+    if (rc != VCR_OK) return rc;
+    KnnTcParams p;
+    p.x = x; p.xx = xx; p.xxmax = xxmax; p.redo = redo; p.nflag = nflag;
+    p.D = D; p.N = N; p.k = k; p.ksel = k + 8 < 31 ? k + 8 : 31; p.KB = (D + 63) / 64;
+    p.idx32 = idx32; p.idx64 = idx64;
+    const size_t smem = knn_tc_smem_bytes(p.KB);
+    if (cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return VCR_ERR_LAUNCH;
+    knn_tc_kernel<<<dim3(vcr_cdiv(N, T2Q), B), T2NT, smem, stream>>>(tm, p);
+    VCR_CHECK_LAUNCH();
+    return launch_knn<16, true>(x, xx, B, D, N, k, idx32, idx64, stream, redo);       // repairs flagged groups only
 }

@@ -96,14 +96,18 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
         h2t = torch.empty_like(h2)
         ops.bgemm(h2, 64, N * 64, 0, trans_feat, 64, 64 * 64, 0, 1, h2t, 64, N * 64, 0, N, 64, 64, B, 1)
         h2 = h2t
-    if idx_feat is None:
-        idx_feat = ops.knn_topk(h2, k, token_major=True)                     # :122 (feature-space kNN)
     tc = config.precision != "fp32"
+    h2_op = ops.to_operand(h2.view(B * N, 64), "h3") if tc else None         # shared by the kNN prefilter and the DG1 GEMM
+    if idx_feat is None:                                                     # :122 (feature-space kNN)
+        if config.use_knn_tc(N) and ops.knn_tc_supported(64, k):
+            idx_feat = ops.knn_topk_tc(h2, h2_op, k)
+        else:
+            idx_feat = ops.knn_topk(h2, k, token_major=True)
     if tc:     # K = 64 / 128 products are output-bandwidth bound: 3-term split on tensor cores in every TC mode
         wpq = packed(m, "pq_h3", [m.convDG1[0].weight, m.convSN1[0].weight],
                      lambda: (ops.to_operand(W["dg1_w"], "h3"), ops.to_operand(W["sn1_w"], "h3")))
         pq1 = torch.empty((B, N, 256), dtype=_F32, device=xyz.device)
-        ops.gemm_tc(ops.to_operand(h2, "h3"), wpq[0], B * N, 256, 64, bias=W["dg1_b"], c=pq1)
+        ops.gemm_tc(h2_op, wpq[0], B * N, 256, 64, bias=W["dg1_b"], c=pq1)
     else:
         pq1 = ops.gemm(h2, W["dg1_w"], W["dg1_b"])                           # [B,N,256] = [P|Q]
     cat = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)

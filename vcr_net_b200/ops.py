@@ -66,6 +66,34 @@ def knn_topk(x: torch.Tensor, k: int, token_major: bool = False, want64: bool = 
     return (idx32, idx64) if want64 else idx32
 
 
+def knn_topk_tc(x: torch.Tensor, xop, k: int, want64: bool = False, want_flagged: bool = False):
+    """Feature-space kNN with the tcgen05 prefilter (csrc/knn.cu): x fp32 token-major [B,N,D], xop its "h3" Operand
+    (None: converted here).  Same (bit-identical) result as knn_topk(x, k, token_major=True).
+    want_flagged: also return the device counter of queries that were recomputed by the exact kernel."""
+    _chk(x, "x")
+    x = x.contiguous()
+    B, N, D = x.shape
+    if xop is None:
+        xop = to_operand(x.view(B * N, D), "h3")
+    assert xop.mode == "h3" and xop.rows == B * N and xop.cols == D
+    L = lib()
+    idx32 = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
+    idx64 = torch.empty((B, N, k), dtype=torch.int64, device=x.device) if want64 else None
+    ws_bytes = L.vcr_knn_tc_workspace_bytes(B, N)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=x.device)
+    L.check(L.vcr_knn_topk_tc(x.data_ptr(), xop.ptr, xop.ld, xop.plane_stride, B, D, N, k, idx32.data_ptr(),
+                              idx64.data_ptr() if want64 else None, ws.data_ptr(), ws_bytes, _stream(x)),
+            "vcr_knn_topk_tc")
+    out = (idx32, idx64) if want64 else (idx32,)
+    if want_flagged:
+        out = out + (ws[-1:],)
+    return out if len(out) > 1 else out[0]
+
+
+def knn_tc_supported(D: int, k: int) -> bool:
+    return 16 <= D <= 128 and D % 4 == 0 and 1 <= k <= 30
+
+
 def graph_feature(xt: torch.Tensor, idx: torch.Tensor):
     """xt token-major [B,N,D], idx int32 [B,N,k] -> [B,2D,N,k] (reference layout)."""
     _chk(xt, "xt"); _chk(idx, "idx", torch.int32)

@@ -9,11 +9,16 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .. import ops
+from .. import config, ops
 
 
 def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     """util/util.py:143-160.  x [B,D,N] -> int64 [B,N,k]; ties -> lower index (canonical order)."""
+    B, D, N = x.shape
+    if config.use_knn_tc(N) and ops.knn_tc_supported(D, k) and N >= k + 1:
+        # feature-space kNN: tcgen05 prefilter + exact re-rank (bit-identical to the FP32 SIMT kernel)
+        _, idx64 = ops.knn_topk_tc(ops.transpose_batched(x.contiguous()), None, k, want64=True)
+        return idx64
     _, idx64 = ops.knn_topk(x, k, token_major=False, want64=True)
     return idx64
 
