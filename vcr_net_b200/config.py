@@ -20,17 +20,23 @@ reuse_target_embedding = os.environ.get("VCR_REUSE_TGT_EMB", "0") == "1"
 
 
 # feature-space kNN (16 <= D <= 128): tcgen05 prefilter + exact re-rank (csrc/knn.cu, bit-identical indices).
-# Measured on B200 (scripts/knn_bench.py, D = 64): 0.73x of the FP32 SIMT kernel at N = 1024 (its 128-candidate tiles cost
-# more sort / merge rounds than the SIMT kernel's 512-candidate tiles save in FMAs), 1.07x at N = 4096, 1.30x at
-# N = 16384.  "auto" (default) therefore uses it from N >= 4096 in the tensor-core precision modes; "1" always, "0" never.
+# Measured on B200 (scripts/knn_bench.py, D = 64, profiles/r01_knn_tc_prefilter_v5.txt): 0.94x of the FP32 SIMT kernel at
+# N = 1024 (two 512-candidate chunks per CTA do not amortise the TMA -> MMA -> TMEM latency chain and the re-rank),
+# 1.47x at N = 4096, 1.85x at N = 16384.  "auto" (default) therefore uses it from N >= 2048 in the tensor-core precision
+# modes; "1" always, "0" never.
 knn_tc = os.environ.get("VCR_KNN_TC", "auto")
-KNN_TC_MIN_N = 4096
+KNN_TC_MIN_N = 2048
 
 
 def use_knn_tc(N: int) -> bool:
     if precision == "fp32" or knn_tc in ("0", False):
         return False
     return True if knn_tc in ("1", True) else N >= KNN_TC_MIN_N
+
+
+# partial-overlap key statistic (model/transformer.py:35-39): the materialised score chunk [cb, h, Nq, Nk] fp32 that
+# feeds the softmax column sums.  Sized to stay L2-resident between the score GEMM and the column-sum kernel.
+stat_chunk_bytes = int(float(os.environ.get("VCR_STAT_CHUNK_MB", "3072")) * (1 << 20))
 
 
 def set_precision(p: str):

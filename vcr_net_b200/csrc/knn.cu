@@ -167,6 +167,45 @@ __device__ __forceinline__ bool filter_merge(const float* drows, const float (&t
     return filter_merge_t<W, TC, TC, TC>(drows, tau, run, buf, j0, lane);
 }
 
+// Selection of one 32-query x 512-candidate distance tile: warp w owns queries QW*w .. QW*w+QW-1, `run` holds their
+// running top-32 lists (one entry per lane), rank `kk` (0-based) is the threshold rank: nothing is dropped unless kk+1
+// seen elements are at least as good, so ranks 0..kk of the final lists are exact.
+__device__ __forceinline__ void select_chunk(const float* dist, uint2* surv, Key (&run)[TQ / (NT / 32)], int j0, int kk,
+                                             int warp, int lane, bool first) {
+    constexpr int QWn = TQ / (NT / 32);
+    uint2* buf = surv + (size_t)warp * TC;
+    const float* drows = dist + (size_t)(warp * QWn) * TC;
+    float tau[QWn];
+    if (first) {
+        float m[QWn];
+#pragma unroll
+        for (int w = 0; w < QWn; ++w) {
+            const float* dr = drows + w * TC + lane;
+            float mm = dr[0];
+#pragma unroll
+            for (int r = 1; r < RPL; ++r) mm = fmaxf(mm, dr[r * 32]);
+            m[w] = mm;
+        }
+        sort32_desc_f<QWn>(m, lane);
+#pragma unroll
+        for (int w = 0; w < QWn; ++w) tau[w] = __shfl_sync(0xffffffffu, m[w], kk);
+    } else {
+#pragma unroll
+        for (int w = 0; w < QWn; ++w) tau[w] = okey_inv(__shfl_sync(0xffffffffu, run[w].hi, kk));
+    }
+    // common case: the survivors of all QW queries fit the warp's buffer and are sorted / merged together
+    if (!filter_merge<QWn>(drows, tau, run, buf, j0, lane)) {
+        // heavy ties (or an adversarial candidate order): one query at a time, any survivor count fits
+#pragma unroll
+        for (int w = 0; w < QWn; ++w) {
+            float t1[1] = {tau[w]};
+            Key r1[1] = {run[w]};
+            filter_merge<1>(drows + w * TC, t1, r1, buf, j0, lane);
+            run[w] = r1[0];
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     const int sz = valid ? 16 : 0;
@@ -303,40 +342,7 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
         __syncthreads();
 
         // ---- selection: warp w owns queries QW*w .. QW*w+QW-1 ------------------------------------------
-        {
-            uint2* buf = surv + (size_t)warp * TC;
-            const float* drows = dist + (size_t)(warp * QW) * TC;
-            float tau[QW];
-            if (j0 == 0) {
-                float m[QW];
-#pragma unroll
-                for (int w = 0; w < QW; ++w) {
-                    const float* dr = drows + w * TC + lane;
-                    float mm = dr[0];
-#pragma unroll
-                    for (int r = 1; r < RPL; ++r) mm = fmaxf(mm, dr[r * 32]);
-                    m[w] = mm;
-                }
-                sort32_desc_f<QW>(m, lane);
-#pragma unroll
-                for (int w = 0; w < QW; ++w) tau[w] = __shfl_sync(0xffffffffu, m[w], k);
-            } else {
-#pragma unroll
-                for (int w = 0; w < QW; ++w)
-                    tau[w] = okey_inv(__shfl_sync(0xffffffffu, run[w].hi, k));
-            }
-            // common case: the survivors of all QW queries fit the warp's buffer and are sorted / merged together
-            if (!filter_merge<QW>(drows, tau, run, buf, j0, lane)) {
-                // heavy ties (or an adversarial candidate order): one query at a time, any survivor count fits
-#pragma unroll
-                for (int w = 0; w < QW; ++w) {
-                    float t1[1] = {tau[w]};
-                    Key r1[1] = {run[w]};
-                    filter_merge<1>(drows + w * TC, t1, r1, buf, j0, lane);
-                    run[w] = r1[0];
-                }
-            }
-        }
+        select_chunk(dist, surv, run, j0, k, warp, lane, j0 == 0);
         // the loop-top __syncthreads orders these smem reads before the next chunk's stores
     }
 
@@ -370,83 +376,51 @@ int launch_knn(const float* x, const float* xx, int B, int D, int N, int k, int3
 }
 
 // =====================================================================================================
-// Tensor-core variant for feature-space kNN (16 <= D <= 128, token-major): tcgen05 distance tiles as a
-// PREFILTER, exact canonical re-rank, certified per query.
+// Tensor-core variant for feature-space kNN (16 <= D <= 128, token-major): the exact kernel's geometry (a CTA owns 32
+// queries, 512-candidate chunks, the same warp-per-query selection) with the FP32 FMA phase replaced by tcgen05
+// distance tiles used as a PREFILTER, then an exact canonical re-rank with a per-query certificate.
 //
-//   approx  dot~_ij from the 3-term fp16 split of the operand-format copy of x (hi*hi' in one TMEM accumulator,
-//           hi*lo' + lo*hi' in a second, combined in fp32), pd~ = (-xx_j - (-2 dot~)) - xx_i with the CANONICAL xx.
-//           A CTA owns 128 queries (UMMA M) and walks the cloud 128 candidates at a time (UMMA N): one TMA
-//           producer / MMA issuer warp, 16 consumer warps that read the 128 x 128 tile from TMEM, write pd~ to a
-//           padded smem tile and run the same warp-per-query threshold filter + shuffle-bitonic merge as the exact
-//           kernel, but keeping ranks 0..ksel (ksel = k + 8) of pd~ instead of 0..k.  MMA of chunk c+1 overlaps
-//           the selection of chunk c.
+//   approx  per chunk 4 MMA tiles D[128 candidates x 32 queries] (candidates on the M side so that a TMEM lane is a
+//           candidate and a thread's 32 columns are the 32 queries: the epilogue's smem stores dist[q][c] are
+//           lane-contiguous).  dot~ from the 3-term fp16 split of the operand-format copy of x (hi*hi' in one TMEM
+//           accumulator, hi*lo' + lo*hi' in a second, combined in fp32); pd~ = (-xx_j - (-2 dot~)) - xx_i with the
+//           CANONICAL xx.  One producer warp (TMA candidate tiles through one smem stage, MMA issue), 8 consumer warps
+//           (TMEM -> pd~ tile -> selection keeping ranks 0..ksel, ksel = k + 8).  The survivor buffers alias the
+//           candidate stage, two CTAs per SM overlap one CTA's TMA/MMA phase with the other's selection.
 //   exact   the 32 list entries of a query are re-evaluated with the canonical fp32 fma chain (one entry per lane)
 //           and sorted by (pd, lower index): ranks 1..k are the answer IF no candidate outside the certified part
 //           of the list can reach rank k:   pd_exact(rank k) > pd~(rank ksel) + eps,   eps >= |pd~ - pd| for this
-//           query against any candidate (bound below).  Otherwise the query's 32-group is flagged and recomputed
-//           by the exact kernel (same launch sequence, no host sync).  The result is therefore bit-identical to
-//           vcr_knn_topk on every input; only the speed depends on the data.
+//           query against any candidate (bound below).  Otherwise the query's 32-group (= this CTA) is flagged and
+//           recomputed by the exact kernel (same launch sequence, no host sync).  The result is therefore
+//           bit-identical to vcr_knn_topk on every input; only the speed depends on the data.
 //   eps     |dot~ - dot_canon| <= (split 3*2^-22 + fp32 chain D*2^-24 + TMEM accumulation D*2^-24) |x_i||x_j|
 //           < 2^-15 |x_i||x_j| for D <= 128; pd doubles it and adds <= 2 ulp of (xx_i + xx_j + 2|dot|):
 //           eps_i = 2^-14 sqrt(xx_i * xxmax) + 2^-20 xxmax, xxmax = max_j xx_j of the cloud.
 //           Clouds with xxmax outside [2^-20, 2^30] (fp16 range of the split) go to the exact kernel entirely.
 // =====================================================================================================
-constexpr int T2Q = 128;                  // queries per CTA
-constexpr int T2C = 128;                  // candidates per chunk
-constexpr int T2LD = T2C + 1;             // padded row stride of the distance tile (conflict-free row-per-thread stores)
-constexpr int T2CAP = 192;                // survivor keys per consumer warp
-constexpr int T2CW = 16;                  // consumer warps
-constexpr int T2NT = (T2CW + 1) * 32;     // + 1 producer warp
-constexpr int T2TILE = 128 * 128;         // bytes of one [128 rows][64 x fp16] swizzled tile
-constexpr int T2QW = 4;                   // queries per selection pass (2 passes per warp)
+constexpr int T2M = 128;                  // candidates per MMA tile (UMMA M)
+constexpr int T2TILES = TC / T2M;         // MMA tiles per chunk (4)
+constexpr int T2NT = NT + 32;             // 8 consumer warps + 1 producer warp
+constexpr int T2CTILE = T2M * 128;        // bytes of one [128 candidates][64 x fp16] swizzled tile
+constexpr int T2QTILE = TQ * 128;         // bytes of one [32 queries][64 x fp16] swizzled tile
 
 struct KnnTcParams {
     const float* x;          // [B, N, D] fp32 token-major
     const float* xx;         // [B*N] canonical squared norms
     const uint32_t* xxmax;   // [B] bit pattern of max_j xx_j
-    int* redo;               // [B * ceil(N/32)] flags for the exact kernel
+    int* redo;               // [B * ceil(N/32)] flags for the exact kernel (one per CTA)
     int* nflag;              // [1] number of uncertified queries (telemetry)
     int D, N, k, ksel, KB;
     int32_t* idx32;
     int64_t* idx64;
 };
 
-__host__ __device__ constexpr size_t knn_tc_smem_bytes(int KB) {
-    return (size_t)2 * KB * 2 * T2TILE + (size_t)T2Q * T2LD * 4 + (size_t)T2CW * T2CAP * 8 + 2 * T2C * 4 + 128 + 1024;
+// smem: Q tiles | candidate stage (aliased by the survivor buffers during selection) | pd~ tile | xx of the queries | barriers
+__host__ __device__ constexpr size_t knn_tc_stage_bytes(int KB) {
+    return (size_t)KB * 2 * T2CTILE > SURV_BYTES ? (size_t)KB * 2 * T2CTILE : SURV_BYTES;
 }
-
-__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(T2CW * 32) : "memory"); }
-
-// one selection pass: 4 queries of this warp against the current 128-candidate tile
-__device__ __forceinline__ void select_pass_tc(const float* drows, Key (&run)[T2QW], uint2* buf, int j0, int ksel,
-                                               int lane, bool first) {
-    float tau[T2QW];
-    if (first) {
-        float m[T2QW];
-#pragma unroll
-        for (int w = 0; w < T2QW; ++w) {
-            const float* dr = drows + w * T2LD + lane;
-            float mm = dr[0];
-#pragma unroll
-            for (int r = 1; r < T2C / 32; ++r) mm = fmaxf(mm, dr[r * 32]);
-            m[w] = mm;
-        }
-        sort32_desc_f<T2QW>(m, lane);
-#pragma unroll
-        for (int w = 0; w < T2QW; ++w) tau[w] = __shfl_sync(0xffffffffu, m[w], ksel);
-    } else {
-#pragma unroll
-        for (int w = 0; w < T2QW; ++w) tau[w] = okey_inv(__shfl_sync(0xffffffffu, run[w].hi, ksel));
-    }
-    if (!filter_merge_t<T2QW, T2C, T2LD, T2CAP>(drows, tau, run, buf, j0, lane)) {
-#pragma unroll
-        for (int w = 0; w < T2QW; ++w) {
-            float t1[1] = {tau[w]};
-            Key r1[1] = {run[w]};
-            filter_merge_t<1, T2C, T2LD, T2CAP>(drows + w * T2LD, t1, r1, buf, j0, lane);
-            run[w] = r1[0];
-        }
-    }
+__host__ __device__ constexpr size_t knn_tc_smem_bytes(int KB) {
+    return (size_t)KB * 2 * T2QTILE + knn_tc_stage_bytes(KB) + (size_t)TQ * TC * 4 + TQ * 4 + 64 + 1024;
 }
 
 __global__ void knn_sqnorm_max_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ xx,
@@ -465,37 +439,38 @@ __global__ void knn_sqnorm_max_kernel(const float* __restrict__ x, int D, int N,
     if ((threadIdx.x & 31) == 0 && bits) atomicMax(xxmax + b, bits);
 }
 
-__global__ void __launch_bounds__(T2NT, 1)
-knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const KnnTcParams p) {
+__global__ void __launch_bounds__(T2NT, 2)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmQ, const KnnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KB = p.KB, N = p.N, D = p.D, k = p.k, ksel = p.ksel;
-    const int opb = KB * 2 * T2TILE;                                   // bytes of one operand block (all k-blocks, hi+lo)
+    const int qbytes = KB * 2 * T2QTILE, cbytes = KB * 2 * T2CTILE;
     uint8_t* q_s = smem;
-    uint8_t* c_s = smem + opb;
-    float* dist = reinterpret_cast<float*>(smem + 2 * opb);            // [128][129]
-    uint2* surv = reinterpret_cast<uint2*>(dist + T2Q * T2LD);         // [16][192]
-    float* xxc_s = reinterpret_cast<float*>(surv + T2CW * T2CAP);      // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xxc_s + 2 * T2C);
+    uint8_t* c_s = smem + qbytes;
+    uint2* surv = reinterpret_cast<uint2*>(c_s);                              // [8][512], valid during selection only
+    float* dist = reinterpret_cast<float*>(c_s + knn_tc_stage_bytes(KB));     // [32][512]
+    float* xxq_s = dist + TQ * TC;                                            // [32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xxq_s + TQ);
     uint64_t* q_full = bars + 0;
-    uint64_t* c_full = bars + 1;
-    uint64_t* mma_done = bars + 2;
-    uint64_t* tmem_empty = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* c_full = bars + 1;          // candidate tile landed                  (4 phases per chunk)
+    uint64_t* mma_bar = bars + 2;         // MMAs of a tile retired: stage reusable (4 phases per chunk)
+    uint64_t* chunk_ready = bars + 3;     // all 4 tiles of the chunk are in TMEM   (1 phase per chunk)
+    uint64_t* stage_free = bars + 4;      // 8 consumer warps finished the chunk's selection (TMEM + stage + dist free)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, q0 = blockIdx.x * T2Q;
-    const int nq32 = (N + 31) / 32;
+    const int b = blockIdx.y, q0 = blockIdx.x * TQ;
     const float* xxb = p.xx + (size_t)b * N;
-    const int nch = (N + T2C - 1) / T2C;
+    const int nch = (N + TC - 1) / TC;
 
-    if (warp == T2CW && lane == 0) {
-        tc::tma_prefetch_desc(&tmX);
-        tc::mbar_init(q_full, 1); tc::mbar_init(c_full, 1); tc::mbar_init(mma_done, 1); tc::mbar_init(tmem_empty, T2CW);
+    if (warp == NT / 32 && lane == 0) {
+        tc::tma_prefetch_desc(&tmC); tc::tma_prefetch_desc(&tmQ);
+        tc::mbar_init(q_full, 1); tc::mbar_init(c_full, 1); tc::mbar_init(mma_bar, 1);
+        tc::mbar_init(chunk_ready, 1); tc::mbar_init(stage_free, NT / 32);
         tc::fence_barrier_init();
     }
     if (warp == 0) { tc::tmem_alloc(tmem_slot, 256); tc::tmem_relinquish(); }
-    if (tid < T2C) xxc_s[tid] = tid < N ? xxb[tid] : 0.f;
+    if (tid < TQ) xxq_s[tid] = q0 + tid < N ? xxb[q0 + tid] : 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -504,117 +479,119 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const KnnTcParams p) {
     const float xm = __uint_as_float(p.xxmax[b]);
     const bool cloud_ok = xm >= 9.5367431640625e-07f && xm <= 1073741824.f;     // [2^-20, 2^30]; false for NaN
     if (!cloud_ok) {
-        // outside the fp16 range of the split: every 32-group of this CTA goes to the exact kernel
-        if (tid < T2Q / 32 && q0 + tid * 32 < N) {
-            p.redo[b * nq32 + q0 / 32 + tid] = 1;
-            atomicAdd(p.nflag, min(32, N - (q0 + tid * 32)));
+        // outside the fp16 range of the split: the exact kernel computes this 32-group
+        if (tid == 0) {
+            p.redo[b * gridDim.x + blockIdx.x] = 1;
+            atomicAdd(p.nflag, min(TQ, N - q0));
         }
-    } else if (warp == T2CW) {
+    } else if (warp == NT / 32) {
         // ============================== TMA producer + MMA issuer ==============================
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc(T2Q, T2C, 0);
+            constexpr uint32_t idesc = tc::umma_idesc(T2M, TQ, 0);
             const int row0 = b * N;
-            tc::mbar_expect_tx(q_full, opb);
+            tc::mbar_expect_tx(q_full, qbytes);
             for (int kb = 0; kb < KB; ++kb)
                 for (int pl = 0; pl < 2; ++pl)
-                    tc::tma_load_3d(q_s + (kb * 2 + pl) * T2TILE, &tmX, q_full, kb * 64, row0 + q0, pl);
-            tc::mbar_expect_tx(c_full, opb);
-            for (int kb = 0; kb < KB; ++kb)
-                for (int pl = 0; pl < 2; ++pl)
-                    tc::tma_load_3d(c_s + (kb * 2 + pl) * T2TILE, &tmX, c_full, kb * 64, row0, pl);
+                    tc::tma_load_3d(q_s + (kb * 2 + pl) * T2QTILE, &tmQ, q_full, kb * 64, row0 + q0, pl);
             tc::mbar_wait(q_full, 0);
             const uint32_t q_addr = tc::smem_u32(q_s), c_addr = tc::smem_u32(c_s);
-            const uint32_t d0 = tmem_base, d1 = tmem_base + T2C;
+            uint32_t g = 0;                                              // tile counter: parity of c_full / mma_bar
             for (int c = 0; c < nch; ++c) {
-                tc::mbar_wait(c_full, c & 1);
-                if (c > 0) tc::mbar_wait(tmem_empty, (c - 1) & 1);
-                tc::tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * 2) * T2TILE);
-                    const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * 2 + 1) * T2TILE);
-                    const uint64_t c_hi = tc::umma_desc_k_sw128(c_addr + (kb * 2) * T2TILE);
-                    const uint64_t c_lo = tc::umma_desc_k_sw128(c_addr + (kb * 2 + 1) * T2TILE);
+                if (c > 0) { tc::mbar_wait(stage_free, (c - 1) & 1); tc::tc_fence_after(); }
+                for (int t = 0; t < T2TILES; ++t, ++g) {
+                    const int cand0 = c * TC + t * T2M;
+                    if (cand0 < N) {
+                        tc::mbar_expect_tx(c_full, cbytes);
+                        for (int kb = 0; kb < KB; ++kb)
+                            for (int pl = 0; pl < 2; ++pl)
+                                tc::tma_load_3d(c_s + (kb * 2 + pl) * T2CTILE, &tmC, c_full, kb * 64, row0 + cand0, pl);
+                        tc::mbar_wait(c_full, g & 1);
+                        tc::tc_fence_after();
+                        const uint32_t d0 = tmem_base + t * TQ, d1 = tmem_base + T2TILES * TQ + t * TQ;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint64_t c_hi = tc::umma_desc_k_sw128(c_addr + (kb * 2) * T2CTILE);
+                            const uint64_t c_lo = tc::umma_desc_k_sw128(c_addr + (kb * 2 + 1) * T2CTILE);
+                            const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * 2) * T2QTILE);
+                            const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * 2 + 1) * T2QTILE);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t acc = (kb | kk) != 0;
-                        const uint64_t adv = (uint64_t)(kk * 2);
-                        tc::umma_f16(d0, q_hi + adv, c_hi + adv, idesc, acc);
-                        tc::umma_f16(d1, q_hi + adv, c_lo + adv, idesc, acc);
-                        tc::umma_f16(d1, q_lo + adv, c_hi + adv, idesc, 1);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint32_t acc = (kb | kk) != 0;
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                tc::umma_f16(d0, c_hi + adv, q_hi + adv, idesc, acc);
+                                tc::umma_f16(d1, c_hi + adv, q_lo + adv, idesc, acc);
+                                tc::umma_f16(d1, c_lo + adv, q_hi + adv, idesc, 1);
+                            }
+                        }
+                        tc::umma_commit(mma_bar);
+                        tc::mbar_wait(mma_bar, g & 1);                   // tile consumed: the stage may be refilled
+                    } else {
+                        // tile entirely past N: nothing to load; keep the barrier phases in step
+                        tc::mbar_arrive(c_full);
+                        tc::mbar_arrive(mma_bar);
                     }
                 }
-                tc::umma_commit(mma_done);
-                tc::mbar_wait(mma_done, c & 1);                      // candidate tile consumed
-                if (c + 1 < nch) {
-                    tc::mbar_expect_tx(c_full, opb);
-                    for (int kb = 0; kb < KB; ++kb)
-                        for (int pl = 0; pl < 2; ++pl)
-                            tc::tma_load_3d(c_s + (kb * 2 + pl) * T2TILE, &tmX, c_full, kb * 64, row0 + (c + 1) * T2C, pl);
-                }
+                tc::umma_commit(chunk_ready);                            // arrives once every MMA of the chunk has retired
             }
         }
     } else {
         // ============================== consumers: TMEM -> pd~ tile -> selection ==============================
-        const int qq = warp & 3, cgp = warp >> 2;
-        const int row = qq * 32 + lane;
-        const uint32_t t_adr = tmem_base + ((uint32_t)(qq * 32) << 16) + cgp * 32;
-        const int qrow = q0 + row;
-        const float xxq_row = qrow < N ? xxb[qrow] : 0.f;
-        uint2* buf = surv + (size_t)warp * T2CAP;
-        Key runA[T2QW], runB[T2QW];
+        const int qq = warp & 3, th = warp >> 2;                         // TMEM lane quarter, tile half
+        Key run[QW];
 #pragma unroll
-        for (int w = 0; w < T2QW; ++w) { runA[w].hi = runA[w].lo = 0u; runB[w].hi = runB[w].lo = 0u; }
+        for (int w = 0; w < QW; ++w) run[w].hi = run[w].lo = 0u;
 
         for (int c = 0; c < nch; ++c) {
-            const int j0 = c * T2C;
-            if (tid < T2C && c + 1 < nch) {
-                const int j = j0 + T2C + tid;
-                xxc_s[((c + 1) & 1) * T2C + tid] = j < N ? xxb[j] : 0.f;
-            }
-            tc::mbar_wait(mma_done, c & 1);
+            const int j0 = c * TC;
+            tc::mbar_wait(chunk_ready, c & 1);
             tc::tc_fence_after();
-            float pdv[32];
-            {
-                const float* xc = xxc_s + (c & 1) * T2C + cgp * 32;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t r0[16], r1[16];
-                    tc::tmem_ld_32x16(t_adr + h * 16, r0);
-                    tc::tmem_ld_32x16(t_adr + T2C + h * 16, r1);
-                    tc::tmem_ld_wait();
+            for (int tt = 0; tt < T2TILES / 2; ++tt) {
+                const int t = th * (T2TILES / 2) + tt;
+                const int cl = t * T2M + qq * 32 + lane;                 // candidate of this thread within the chunk
+                const int j = j0 + cl;
+                float* dcol = dist + cl;
+                if (j0 + t * T2M < N) {                                  // warp-uniform: the tile holds data
+                    const uint32_t ta = tmem_base + ((uint32_t)(qq * 32) << 16) + t * TQ;
+                    const bool cvalid = j < N;
+                    const float nxc = cvalid ? -xxb[j] : 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float dot = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
-                        pdv[h * 16 + i] = __fsub_rn(__fsub_rn(-xc[h * 16 + i], -2.f * dot), xxq_row);
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t r0[16], r1[16];
+                        tc::tmem_ld_32x16(ta + h * 16, r0);
+                        tc::tmem_ld_32x16(ta + T2TILES * TQ + h * 16, r1);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const float dot = fmaf(__uint_as_float(r1[q]), 1.f / 2048.f, __uint_as_float(r0[q]));
+                            const float pd = __fsub_rn(__fsub_rn(nxc, -2.f * dot), xxq_s[h * 16 + q]);
+                            dcol[(h * 16 + q) * TC] = cvalid ? pd : -INFINITY;
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < TQ; ++q) dcol[q * TC] = -INFINITY;
                 }
             }
             tc::tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");       // pd~ tile complete (consumer warps only)
+            select_chunk(dist, surv, run, j0, ksel, warp, lane, c == 0);
+            tc::fence_proxy_async();                                     // survivor stores (generic proxy) before the next TMA fill
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(tmem_empty);              // the MMA of chunk c+1 may overwrite TMEM
-            {
-                float* drow = dist + row * T2LD + cgp * 32;
-                const int jc = j0 + cgp * 32;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) drow[i] = (jc + i < N) ? pdv[i] : -INFINITY;
-            }
-            cons_bar();
-            select_pass_tc(dist + (size_t)(warp * 8) * T2LD, runA, buf, j0, ksel, lane, c == 0);
-            select_pass_tc(dist + (size_t)(warp * 8 + T2QW) * T2LD, runB, buf, j0, ksel, lane, c == 0);
-            cons_bar();                                              // tile reads done before the next chunk's stores
+            if (lane == 0) tc::mbar_arrive(stage_free);
         }
 
         // ---- exact re-rank + certificate, one query at a time, one list entry per lane ----
         const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+        bool all_safe = true;
 #pragma unroll
-        for (int qi = 0; qi < 2 * T2QW; ++qi) {
-            const int q = q0 + warp * 8 + qi;
-            if (q >= N) continue;                                    // warp-uniform
-            const Key a = qi < T2QW ? runA[qi & 3] : runB[qi & 3];
+        for (int qi = 0; qi < QW; ++qi) {
+            const int q = q0 + warp * QW + qi;
+            if (q >= N) continue;                                        // warp-uniform
+            const Key a = run[qi];
             const uint32_t thr_hi = __shfl_sync(0xffffffffu, a.hi, ksel);
             const int j = (int)(~a.lo);
             const bool valid = j >= 0 && j < N;
-            const float xxq = xxb[q];
+            const float xxq = xxq_s[warp * QW + qi];
             Key e[1];
             e[0].hi = 0u; e[0].lo = 0u;
             if (valid) {
@@ -645,17 +622,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const KnnTcParams p) {
                     if (p.idx32) p.idx32[o] = jn;
                     if (p.idx64) p.idx64[o] = (int64_t)jn;
                 }
-            } else if (lane == 0) {
-                p.redo[b * nq32 + q / 32] = 1;
-                atomicAdd(p.nflag, 1);
+            } else {
+                all_safe = false;
+                if (lane == 0) atomicAdd(p.nflag, 1);
             }
         }
+        if (!all_safe && lane == 0) p.redo[b * gridDim.x + blockIdx.x] = 1;
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
 }
-
 
 }  // namespace
 
@@ -707,8 +684,10 @@ VCR_API int vcr_knn_topk_tc(const float* x, const void* xop, int ld, long long p
     dim3 g(vcr_cdiv(N, 256), B);
     knn_sqnorm_max_kernel<<<g, 256, 0, stream>>>(x, D, N, xx, xxmax);
     VCR_CHECK_LAUNCH();
-    CUtensorMap tm;
-    int rc = vcr_make_operand_tmap(&tm, xop, D, (long long)B * N, ld, plane_stride, 2, T2Q);
+    CUtensorMap tmC, tmQ;
+    int rc = vcr_make_operand_tmap(&tmC, xop, D, (long long)B * N, ld, plane_stride, 2, T2M);
+    if (rc != VCR_OK) return rc;
+    rc = vcr_make_operand_tmap(&tmQ, xop, D, (long long)B * N, ld, plane_stride, 2, TQ);
     if (rc != VCR_OK) return rc;
     KnnTcParams p;
     p.x = x; p.xx = xx; p.xxmax = xxmax; p.redo = redo; p.nflag = nflag;
@@ -717,7 +696,7 @@ VCR_API int vcr_knn_topk_tc(const float* x, const void* xop, int ld, long long p
     const size_t smem = knn_tc_smem_bytes(p.KB);
     if (cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return VCR_ERR_LAUNCH;
-    knn_tc_kernel<<<dim3(vcr_cdiv(N, T2Q), B), T2NT, smem, stream>>>(tm, p);
+    knn_tc_kernel<<<dim3(nq32, B), T2NT, smem, stream>>>(tmC, tmQ, p);
     VCR_CHECK_LAUNCH();
     return launch_knn<16, true>(x, xx, B, D, N, k, idx32, idx64, stream, redo);       // repairs flagged groups only
 }

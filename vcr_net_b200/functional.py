@@ -514,7 +514,7 @@ def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
         # partial overlap (:35-53): column sums of the unmasked probabilities pick the surviving keys.
         # This one statistic still goes through materialised scores (chunked); the attention itself is flash.
         ldS = (Nk + 3) // 4 * 4
-        cb = max(1, min(B, max_ws_bytes // (h * Nq * ldS * 4)))
+        cb = max(1, min(B, min(max_ws_bytes, config.stat_chunk_bytes) // (h * Nq * ldS * 4)))
         S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
         csum = torch.empty((B, Nk), dtype=_F32, device=dev)
         for b0 in range(0, B, cb):
