@@ -5,7 +5,7 @@ Same class / function names as the reference's ``model`` and ``util`` packages
 farthest_point_sample, transform_point_cloud, quat2mat); the compute runs in hand-written
 CUDA kernels behind the C ABI of include/vcr_b200.h.  There is no CPU fallback.
 """
-from .model.lpdnet_model import LPD, LPDNet  # noqa: F401
+from .model.lpdnet_model import LPD, LPDNet, TranformNet  # noqa: F401
 from .model.icp_model import ICP  # noqa: F401
 from .model.transformer import Transformer  # noqa: F401
 from .model.vcrnet_model import (DGCNN, PointNet, SVDHead, VcpAtt, VcpByDis, VcpTopK, VCRNet,  # noqa: F401

@@ -17,7 +17,7 @@ import sys
 HOT_PATH = {
     "model.vcrnet_model": ["VCRNet", "VcpTopK", "VcpAtt", "VcpByDis", "SVDHead", "Identity", "vcrnetIter", "vcrnetIcpNet", "DGCNN",
                            "PointNet"],
-    "model.lpdnet_model": ["LPDNet", "LPD"],
+    "model.lpdnet_model": ["LPDNet", "LPD", "TranformNet"],
     "model.icp_model": ["ICP"],
     "model.transformer": ["Transformer", "MultiHeadedAttention", "PositionwiseFeedForward", "LayerNorm",
                           "EncoderDecoder", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer",
