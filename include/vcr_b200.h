@@ -165,6 +165,12 @@ int vcr_sqnorm_rows(const float* X, int ld, long long rows, int D, float* out, c
 int vcr_softcorr_rows(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
                       const float* tgt, int mode, float* corr, int* best_idx, float* best_val, cudaStream_t stream);
 int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy, cudaStream_t stream);
+/* getCopairALL (:334-347) fused on tensor cores: S / T operand-format ("h3", 2 planes) embeddings [2][B*Ns][lds] /
+ * [2][B*Nt][ldt], xx / yy their fp32 squared row norms, tgt [B,3,Nt] -> corr [B,3,Ns] = softmax_j(pd_ij) tgt_j with the
+ * reference's pd operation order; the [Ns,Nt] score matrix never reaches HBM (online softmax in the GEMM epilogue). */
+int vcr_softcorr_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
+                    const float* xx, const float* yy, const float* tgt, int B, int Ns, int Nt, int D,
+                    float* corr, cudaStream_t stream);
 /* row sums of the softmax taken over sources (dim=1) (:243-244); workspace from the size query. */
 size_t vcr_rowsum_colsoftmax_workspace_bytes(int B, int Nt);
 int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,

@@ -378,6 +378,51 @@ def test_vcp_head_vs_golden(net_whole, net_partial, precision):
     assert got.shape == want.shape and _col_set_diff(got, want) <= 2
 
 
+def _copair_all_f64(se, te, tgt):
+    se, te, tgt = se.astype(np.float64), te.astype(np.float64), tgt.astype(np.float64)
+    pd = 2.0 * np.matmul(se.transpose(0, 2, 1), te) - (se ** 2).sum(1)[:, :, None] - (te ** 2).sum(1)[:, None, :]
+    pd -= pd.max(-1, keepdims=True)
+    P = np.exp(pd)
+    P /= P.sum(-1, keepdims=True)
+    return np.matmul(tgt, P.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("B,Ns,Nt,D,common", [(2, 200, 333, 512, 0.0), (2, 200, 333, 512, 0.8), (3, 1024, 1024, 512, 0.8),
+                                              (1, 129, 64, 128, 0.0), (2, 768, 500, 64, 0.3), (1, 2048, 4096, 512, 0.8)])
+def test_fused_softcorr_vs_oracle_and_row_pass(B, Ns, Nt, D, common):
+    """csrc/softcorr_tc.cu (GEMM + online softmax + weighted target sum in one kernel, no score matrix in HBM) against the
+    numpy oracle's getCopairALL, a float64 evaluation of the same formula, and the materialised GEMM -> row-pass path,
+    incl. ragged / unequal sizes.  common > 0: embeddings share a large component (|f|^2 >> gaps, the cancellation regime
+    of the real network): there every fp32 evaluation -- the oracle's included -- carries ~|f|^2 * 2^-23
+    of logit noise, so the bar is "as close to float64 as the fp32 oracle is", plus fused == row pass."""
+    from vcr_net_b200 import config, functional as Fn
+    rs = np.random.RandomState(B + Ns + Nt)
+    base = rs.randn(1, D, 1).astype(np.float32) * common
+    se = (base + 0.05 * rs.randn(B, D, Ns)).astype(np.float32)
+    te = (base + 0.05 * rs.randn(B, D, Nt)).astype(np.float32)
+    src = rs.rand(B, 3, Ns).astype(np.float32) - 0.5
+    tgt = rs.rand(B, 3, Nt).astype(np.float32) - 0.5
+    _, want = O.get_copair_all(src, se, tgt, te)
+    truth = _copair_all_f64(se, te, tgt)
+    s_tok, t_tok = cu(np.ascontiguousarray(se.transpose(0, 2, 1))), cu(np.ascontiguousarray(te.transpose(0, 2, 1)))
+    old_p, old_f = config.precision, config.fused_softcorr
+    try:
+        config.set_precision("h3")
+        config.fused_softcorr = True
+        fused = nump(Fn.vcp_whole(s_tok, t_tok, cu(tgt)))
+        config.fused_softcorr = False
+        rows = nump(Fn.vcp_whole(s_tok, t_tok, cu(tgt)))
+    finally:
+        config.set_precision(old_p)
+        config.fused_softcorr = old_f
+    assert fused.shape == want.shape == (B, 3, Ns)
+    assert rel_err(fused, rows) < 2e-5                       # same products, same pd op order; only the softmax schedule differs
+    bar = max(TOL, 2.0 * rel_err(want, truth))               # fp32 oracle's own distance from float64
+    assert rel_err(fused, truth) < bar and rel_err(rows, truth) < bar, (rel_err(fused, truth), rel_err(want, truth))
+    if common == 0.0:
+        assert rel_err(fused, want) < TOL
+
+
 def test_svd_head_vs_golden(net_whole):
     g = load_golden("svd_head")
     R, t = net_whole.svd(cu(g["src"]), cu(g["corr"]))

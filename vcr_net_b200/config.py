@@ -39,6 +39,11 @@ def use_knn_tc(N: int) -> bool:
 stat_chunk_bytes = int(float(os.environ.get("VCR_STAT_CHUNK_MB", "3072")) * (1 << 20))
 
 
+# whole-to-whole VCP head (getCopairALL): fused tcgen05 GEMM + online softmax + weighted target sum (csrc/softcorr_tc.cu)
+# instead of GEMM -> HBM score matrix -> row pass (tensor-core precision modes)
+fused_softcorr = os.environ.get("VCR_FUSED_SOFTCORR", "1") != "0"
+
+
 def set_precision(p: str):
     global precision
     if p not in VALID:

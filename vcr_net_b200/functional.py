@@ -618,8 +618,12 @@ def vcp_whole(src_tok, tgt_tok, tgt_xyz):
     """getCopairALL (model/vcrnet_model.py:334-347): src_corr [B,3,N]."""
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
-    dot, ld = pair_dots(src_tok, tgt_tok)
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
+    if config.precision != "fp32" and config.fused_softcorr:
+        # one kernel: 3-term tcgen05 products + online softmax + weighted sum of the target points in the epilogue
+        return ops.softcorr_tc(ops.to_operand(src_tok.reshape(B * Ns, D), "h3"), ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3"),
+                               xx, yy, tgt_xyz, B, Ns, Nt, D)
+    dot, ld = pair_dots(src_tok, tgt_tok)
     corr, _, _ = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=tgt_xyz.contiguous(), mode=0)
     return corr
 

@@ -569,6 +569,19 @@ def softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=None, mode=0):
     return corr, best_i, best_v
 
 
+def softcorr_tc(s_op: "Operand", t_op: "Operand", xx, yy, tgt_xyz: torch.Tensor, B: int, Ns: int, Nt: int, D: int):
+    """Fused getCopairALL on tensor cores (csrc/softcorr_tc.cu): corr [B,3,Ns]; no [Ns,Nt] matrix in HBM."""
+    assert s_op.mode == "h3" and t_op.mode == "h3" and s_op.rows == B * Ns and t_op.rows == B * Nt
+    tgt_xyz = tgt_xyz.contiguous()
+    _chk(tgt_xyz, "tgt")
+    corr = torch.empty((B, 3, Ns), dtype=_F32, device=tgt_xyz.device)
+    L = lib()
+    L.check(L.vcr_softcorr_tc(s_op.ptr, s_op.ld, s_op.plane_stride, t_op.ptr, t_op.ld, t_op.plane_stride,
+                              xx.data_ptr(), yy.data_ptr(), tgt_xyz.data_ptr(), B, Ns, Nt, D, corr.data_ptr(),
+                              _stream(tgt_xyz)), "vcr_softcorr_tc")
+    return corr
+
+
 def negdist_(dot, ld, Ns, Nt, xx, yy):
     B = dot.shape[0]
     L = lib()
