@@ -1,3 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "softcorr" > gpurun_out/dev_sc_pytest.log 2>&1; tail -15 gpurun_out/dev_sc_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/dev_pytest_gpu.log 2>&1; tail -8 gpurun_out/dev_pytest_gpu.log
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/dev_bench_partial.json 2>gpurun_out/dev_bench_partial.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/dev_bench_partial.json"))
+print("partial", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "whole", {k:round(v["value"],1) for k,v in d.get("other_workloads",{}).items()})
+PY

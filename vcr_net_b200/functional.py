@@ -560,14 +560,23 @@ def _ln_op(norm, x, mode):
     return ops.layernorm_operand(x, norm.a_2, norm.b_2, norm.eps, mode)
 
 
-def encoder_decoder_tc(model, src, tgt, final_residual, mode):
+def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False):
+    """swap_mem: decoder batch item b attends to the encoder output of item (b + B/2) mod B -- the two directions of
+    Transformer.forward run as one batch [src; tgt] without building the swapped copy [tgt; src]: only the encoder's
+    final LayerNorm writes its two halves exchanged."""
     B, Ns, D = src.shape
     Nt = tgt.shape[1]
     x = src
     for layer in model.encoder.layers:
         x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, Ns, Ns, x, mode)
         x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * Ns, x, mode)
-    mem = _ln_op(model.encoder.norm, x, mode)
+    if swap_mem:
+        half, nrm = B // 2, model.encoder.norm
+        mem = ops.Operand.empty(B * Ns, D, mode, src.device)
+        ops.layernorm_operand(x[:half], nrm.a_2, nrm.b_2, nrm.eps, mode, out=mem.rows_view(half * Ns, half * Ns))
+        ops.layernorm_operand(x[half:], nrm.a_2, nrm.b_2, nrm.eps, mode, out=mem.rows_view(0, half * Ns))
+    else:
+        mem = _ln_op(model.encoder.norm, x, mode)
     y = tgt
     for layer in model.decoder.layers:
         y = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, y, mode), None, B, Nt, Nt, y, mode)
@@ -583,7 +592,17 @@ def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_inp
     VCRNet residual (vcrnet_model.py:504-505) is fused: (src+src_p, tgt+tgt_p)."""
     B = src_tok.shape[0]
     if src_tok.shape[1] == tgt_tok.shape[1]:
-        enc_in = torch.cat([src_tok, tgt_tok], dim=0)
+        if (src_tok.is_contiguous() and tgt_tok.is_contiguous() and src_tok.untyped_storage().data_ptr() ==
+                tgt_tok.untyped_storage().data_ptr() and
+                tgt_tok.storage_offset() == src_tok.storage_offset() + src_tok.numel()):
+            # the two halves of one embedding batch (VCRNet.forward): [src; tgt] already exists, no copy
+            enc_in = src_tok.as_strided((2 * B,) + tuple(src_tok.shape[1:]), src_tok.stride(), src_tok.storage_offset())
+        else:
+            enc_in = torch.cat([src_tok, tgt_tok], dim=0)
+        if config.precision != "fp32":
+            enc_in = enc_in.contiguous()
+            out = encoder_decoder_tc(tr.model, enc_in, enc_in, enc_in if add_input else None, config.precision, swap_mem=True)
+            return out[:B], out[B:]
         dec_in = torch.cat([tgt_tok, src_tok], dim=0)
         out = encoder_decoder_tok(tr.model, enc_in, dec_in, final_residual=dec_in if add_input else None)
         return out[B:], out[:B]

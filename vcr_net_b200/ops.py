@@ -246,10 +246,12 @@ def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, N
     return out
 
 
-def layernorm_operand(x: torch.Tensor, a, b, eps, mode) -> Operand:
+def layernorm_operand(x: torch.Tensor, a, b, eps, mode, out: Operand | None = None) -> Operand:
     _chk(x, "x")
     M, D, ldx = _rows(x)
-    out = Operand.empty(M, D, mode, x.device)
+    if out is None:
+        out = Operand.empty(M, D, mode, x.device)
+    assert out.rows == M and out.cols == D and out.mode == mode
     L = lib()
     L.check(L.vcr_layernorm_operand(x.data_ptr(), ldx, a.data_ptr(), b.data_ptr(), float(eps), M, D, out.ptr,
                                     out.ld, out.plane_stride, out.planes, int(mode == "bf16"), _stream(x)),
