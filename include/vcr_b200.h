@@ -147,6 +147,14 @@ int vcr_row_lse(const float* S, int ld, long long rows, int n, const uint8_t* ke
 int vcr_softmax_operand(const float* S, int ld, long long rows, int n, const uint8_t* keep,
                         long long rows_per_batch, void* out, int ldo, long long plane_stride, int planes,
                         int bf16, cudaStream_t stream);
+/* The same statistic straight from the operand-format Q / K projections (model/transformer.py:33-39), nothing of size
+ * Nq x Nk in HBM: per (batch, head, 128-query tile) two tcgen05 sweeps over the key tiles (row max / sum, then the
+ * normalised probabilities summed over the tile's rows), partials reduced in a fixed order.  Q: [2 planes][B*Nq][ldq]
+ * with head hh in columns [hh*128, +128), K likewise; d_k = 128; out [B, Nk]. */
+size_t vcr_attn_colsum_workspace_bytes(int B, int H, int Nq, int Nk);
+int vcr_attn_colsum_tc(const void* Q, int ldq, long long q_plane, const void* K, int ldk, long long k_plane,
+                       int B, int H, int Nq, int Nk, int dk, float scale, float* out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 /* fused, single-read form of vcr_row_lse + vcr_colsum_softmax (unmasked): out[B,n] = column sums of softmax rows */
 size_t vcr_softmax_colsum_workspace_bytes(int B, long long rows_per_batch, int ld, int n);
 int vcr_softmax_colsum(const float* S, int ld, int B, long long rows_per_batch, int n, float* out,

@@ -762,6 +762,35 @@ def test_fused_softmax_colsum(B, rpb, n):
     assert np.array_equal(nump(ops.colsum_softmax(S, n, B, fused=True)), got)      # deterministic
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 4, 200, 333), (3, 4, 768, 768), (1, 2, 129, 64), (1, 4, 1024, 2048), (2, 1, 50, 130)])
+def test_attn_colsum_tc_two_sweep_statistic(B, H, Nq, Nk):
+    """csrc/attn_colsum_tc.cu (partial-overlap key statistic, model/transformer.py:33-39, no score matrix in HBM) vs a
+    float64 evaluation and vs the materialised score-GEMM -> column-sum path; ragged / unequal sizes; deterministic."""
+    import math
+    dk = 128
+    rs = np.random.RandomState(B * 7 + Nq + Nk)
+    q = rs.randn(B * Nq, H * dk).astype(np.float32)
+    k = rs.randn(B * Nk, H * dk).astype(np.float32)
+    scale = 1.0 / math.sqrt(dk)
+    q4 = q.astype(np.float64).reshape(B, Nq, H, dk).transpose(0, 2, 1, 3)
+    k4 = k.astype(np.float64).reshape(B, Nk, H, dk).transpose(0, 2, 1, 3)
+    sc = np.matmul(q4, k4.transpose(0, 1, 3, 2)) * scale
+    pr = np.exp(sc - sc.max(-1, keepdims=True))
+    want = (pr / pr.sum(-1, keepdims=True)).sum(axis=(1, 2))                       # [B, Nk]
+    qo, ko = ops.to_operand(cu(q), "h3"), ops.to_operand(cu(k), "h3")
+    got = ops.attn_colsum_tc(qo, ko, B, H, Nq, Nk, dk, scale)
+    assert tuple(got.shape) == (B, Nk)
+    assert rel_err(nump(got), want) < 1e-5
+    assert torch.equal(ops.attn_colsum_tc(qo, ko, B, H, Nq, Nk, dk, scale), got)   # deterministic
+    # the path it replaces: scaled scores through the GEMM kernel, then the single-read column-sum kernel
+    ldS = (Nk + 3) // 4 * 4
+    S = torch.zeros((B, H, Nq, ldS), dtype=torch.float32, device=DEV)
+    ops.gemm_tc(qo, ko, Nq, Nk, dk, nbo=B, nbi=H, a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
+                c_strides=(H * Nq * ldS, Nq * ldS))
+    old = ops.colsum_softmax(S.view(B * H * Nq, ldS), Nk, B)
+    assert rel_err(nump(got), nump(old)) < 1e-5
+
+
 def test_vcrnet_iter_target_embedding_reuse_is_bit_identical(net_partial):
     """config.reuse_target_embedding hoists the loop-invariant emb_nn(tgt) out of the --iter loop: same bits out."""
     from vcr_net_b200 import config

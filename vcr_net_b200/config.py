@@ -44,6 +44,10 @@ stat_chunk_bytes = int(float(os.environ.get("VCR_STAT_CHUNK_MB", "3072")) * (1 <
 fused_softcorr = os.environ.get("VCR_FUSED_SOFTCORR", "1") != "0"
 
 
+# partial-overlap key statistic: two-sweep tcgen05 kernel (csrc/attn_colsum_tc.cu) instead of score GEMM -> HBM -> column sums
+fused_key_stat = os.environ.get("VCR_FUSED_KEY_STAT", "1") != "0"
+
+
 def set_precision(p: str):
     global precision
     if p not in VALID:

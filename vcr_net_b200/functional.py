@@ -513,16 +513,20 @@ def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
     if m.is_src:
         # partial overlap (:35-53): column sums of the unmasked probabilities pick the surviving keys.
         # This one statistic still goes through materialised scores (chunked); the attention itself is flash.
-        ldS = (Nk + 3) // 4 * 4
-        cb = max(1, min(B, min(max_ws_bytes, config.stat_chunk_bytes) // (h * Nq * ldS * 4)))
-        S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
-        csum = torch.empty((B, Nk), dtype=_F32, device=dev)
-        for b0 in range(0, B, cb):
-            nb = min(cb, B - b0)
-            ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
-                        a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
-                        c_strides=(h * Nq * ldS, Nq * ldS))
-            csum[b0:b0 + nb] = ops.colsum_softmax(S[:nb].view(nb * h * Nq, ldS), Nk, nb)
+        if dk == 128 and mode == "h3" and config.fused_key_stat:
+            # two tcgen05 sweeps per (batch, head, query tile): no score matrix in HBM (csrc/attn_colsum_tc.cu)
+            csum = ops.attn_colsum_tc(q_v, k_v, B, h, Nq, Nk, dk, scale)
+        else:
+            ldS = (Nk + 3) // 4 * 4
+            cb = max(1, min(B, min(max_ws_bytes, config.stat_chunk_bytes) // (h * Nq * ldS * 4)))
+            S = torch.empty((cb, h, Nq, ldS), dtype=_F32, device=dev)
+            csum = torch.empty((B, Nk), dtype=_F32, device=dev)
+            for b0 in range(0, B, cb):
+                nb = min(cb, B - b0)
+                ops.gemm_tc(q_v.rows_view(b0 * Nq, nb * Nq), k_v.rows_view(b0 * Nk, nb * Nk), Nq, Nk, dk, nbo=nb, nbi=h,
+                            a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
+                            c_strides=(h * Nq * ldS, Nq * ldS))
+                csum[b0:b0 + nb] = ops.colsum_softmax(S[:nb].view(nb * h * Nq, ldS), Nk, nb)
         _, keep = ops.topk_select(csum, int(Nk * m.overlap2), want_idx=False, want_mask=True)
     if dk == 128 and config.flash_attention:
         ops.flash_attn_tc(q_v, k_v, vt, att, B, h, Nq, Nk, dk, scale, keep=keep)

@@ -246,6 +246,19 @@ def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, N
     return out
 
 
+def attn_colsum_tc(q: Operand, k: Operand, B, H, Nq, Nk, dk, scale):
+    """Column sums over heads and queries of softmax(Q K^T * scale) -> [B, Nk]; scores never reach HBM."""
+    assert q.mode == "h3" and k.mode == "h3"
+    dev = q.buf.device
+    L = lib()
+    wsb = L.vcr_attn_colsum_workspace_bytes(B, H, Nq, Nk)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out = torch.empty((B, Nk), dtype=_F32, device=dev)
+    L.check(L.vcr_attn_colsum_tc(q.ptr, q.ld, q.plane_stride, k.ptr, k.ld, k.plane_stride, B, H, Nq, Nk, dk,
+                                 float(scale), out.data_ptr(), ws.data_ptr(), wsb, _stream(q.buf)), "vcr_attn_colsum_tc")
+    return out
+
+
 def layernorm_operand(x: torch.Tensor, a, b, eps, mode, out: Operand | None = None) -> Operand:
     _chk(x, "x")
     M, D, ldx = _rows(x)
