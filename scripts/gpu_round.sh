@@ -15,10 +15,15 @@ cat gpurun_out/bench_lpd_train.json; tail -3 gpurun_out/bench_lpd_train.err
 timeout 300 python scripts/step_profile.py h3 > gpurun_out/step_profile_h3.txt 2>&1
 cat gpurun_out/step_profile_h3.txt
 timeout 300 python scripts/step_profile.py h3 partial > gpurun_out/step_profile_partial_h3.txt 2>&1
+# BASELINE config 4 (scaled inference, 4096 pts, 256 pairs over 8 GPUs = 32 per GPU) and config 5 (kernel sweep)
+timeout 600 python bench.py --steps 5 --warmup 3 --workload whole --num-points 4096 --batch 32 --no-cpu-baseline --no-other-workloads > gpurun_out/bench_whole_4096_b32.json 2> gpurun_out/bench_whole_4096_b32.err
+cat gpurun_out/bench_whole_4096_b32.json; tail -3 gpurun_out/bench_whole_4096_b32.err
+timeout 300 python scripts/knn_bench.py > gpurun_out/knn_bench.txt 2>&1
+timeout 600 python scripts/kernel_sweep.py > gpurun_out/kernel_sweep_cfg5.txt 2>&1
 if [ "$1" != "nonc" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_h3.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_launch.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_h3.csv > gpurun_out/launches_h3_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|flash_attn|knn_select|edgeconv_dg_tc' -s 60 -c 24 \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|flash_attn|knn_select|edgeconv_dg_tc|attn_colsum|softcorr_tc' -s 60 -c 28 \
     -f -o gpurun_out/prof_h3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_full.log 2>&1
 fi

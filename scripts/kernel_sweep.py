@@ -37,6 +37,9 @@ for N in (512, 1024, 2048, 4096, 8192, 16384):
     ms = timeit(lambda: ops.knn_topk(f, 20, token_major=True))
     fl = 2.0 * 64 * N * N * B
     print(f"knn_topk_64d, {N}, {B}, {ms*1e3:.1f}, {fl/ms/1e9:.2f}, TFLOP/s fp32, {fl/ms/1e9/FMA:.3f}, of fp32 FMA peak")
+    fop = ops.to_operand(f.view(B * N, 64), "h3")
+    ms_tc = timeit(lambda: ops.knn_topk_tc(f, fop, 20))
+    print(f"knn_topk_64d_tc_prefilter, {N}, {B}, {ms_tc*1e3:.1f}, {ms/ms_tc:.2f}, x vs SIMT, , tcgen05 distance tiles + exact re-rank (bit-identical); selection-bound")
     ms = timeit(lambda: ops.knn_topk(x, 20, token_major=False))
     print(f"knn_topk_3d, {N}, {B}, {ms*1e3:.1f}, {B*N*N/ms/1e6:.1f}, Gpair/s, , selection-bound ({2.0*3*N*N*B/ms/1e9:.2f} TFLOP/s)")
     # --- flash attention (4 heads x 128) --------------------------------------------------------------------
@@ -55,7 +58,7 @@ for N in (512, 1024, 2048, 4096, 8192, 16384):
     txyz = torch.rand(Bs, 3, N, device=dev)
     ms = timeit(lambda: Fn.vcp_whole(s_tok, t_tok, txyz))
     fl = (2.0 * 512 + 6) * N * N * Bs
-    print(f"softcorr_whole, {N}, {Bs}, {ms*1e3:.1f}, {fl/ms/1e9:.1f}, TFLOP/s algorithmic, {fl/ms/1e9/TC:.3f}, GEMM(3-term) + row pass; score matrix {4.0*N*N*Bs/1e6:.0f} MB")
+    print(f"softcorr_whole, {N}, {Bs}, {ms*1e3:.1f}, {fl/ms/1e9:.1f}, TFLOP/s algorithmic, {fl/ms/1e9/TC:.3f}, fused tcgen05 GEMM + online softmax + weighted target sum (no {4.0*N*N*Bs/1e6:.0f} MB score matrix in HBM); tensor work = 3x: {3*fl/ms/1e9/TC:.3f}")
     # --- SVD head -------------------------------------------------------------------------------------------
     for Bp in (1, 16, 256):
         a = torch.rand(Bp, 3, N, device=dev); b = torch.rand(Bp, 3, N, device=dev)
