@@ -5,7 +5,8 @@ import csv, json, re, sys, collections
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
 FAMILY = [("gemm_tc_kernel", "vcr_gemm_tc"), ("flash_attn_tc_kernel", "vcr_flash_attn_tc"), ("knn_select_kernel", "vcr_knn_topk"),
-          ("knn_topk_kernel", "vcr_knn_topk"), ("edgeconv_dg_tc_kernel", "vcr_edgeconv_dg_tc")]
+          ("knn_topk_kernel", "vcr_knn_topk"), ("edgeconv_dg_tc_kernel", "vcr_edgeconv_dg_tc"),
+          ("attn_colsum_tc_kernel", "vcr_attn_colsum_tc"), ("softcorr_tc_kernel", "vcr_softcorr_tc"), ("knn_tc_kernel", "vcr_knn_topk_tc")]
 agg = collections.OrderedDict()
 for path in sys.argv[1:]:
     rows = list(csv.reader(open(path)))
