@@ -130,6 +130,11 @@ int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, const int* 
  * LayerNorm (:134-144): a*(x-mean)/(std_unbiased+eps)+b (+ residual if not NULL). D%128==0, D<=1024. */
 int vcr_layernorm(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
                   const float* residual, int ldr, float* out, int ldo, cudaStream_t stream);
+/* the same, additionally writing the operand-format copy [2 planes][M][ldop] (fp16 hi, lo * 2^11) and the squared row
+ * norms sq[M] of `out` (what the VCP head, model/vcrnet_model.py:337-339, derives from the Transformer output). */
+int vcr_layernorm_head(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                       const float* residual, int ldr, float* out, int ldo, void* op, int ldop,
+                       long long plane_stride, float* sq, cudaStream_t stream);
 /* softmax over the last dim, in place (:34); keep[batch,n]==0 keys are set to -1e9 first (:51-52). */
 int vcr_softmax_rows(float* S, int ld, long long rows, int n, const uint8_t* keep, long long rows_per_batch,
                      cudaStream_t stream);
@@ -179,6 +184,11 @@ int vcr_negdist(float* dot, int ld, int B, int Ns, int Nt, const float* xx, cons
 int vcr_softcorr_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
                     const float* xx, const float* yy, const float* tgt, int B, int Ns, int Nt, int D,
                     float* corr, cudaStream_t stream);
+/* getCopair (:264-332) through the same fused kernel: best_idx[B,Ns] = argmax_j pd_ij (ties -> lower j),
+ * best_val[B,Ns] = max_j softmax_j(pd_ij) -- the hard correspondences of the partial path. */
+int vcr_softcorr_best_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
+                         const float* xx, const float* yy, int B, int Ns, int Nt, int D,
+                         int* best_idx, float* best_val, cudaStream_t stream);
 /* row sums of the softmax taken over sources (dim=1) (:243-244); workspace from the size query. */
 size_t vcr_rowsum_colsoftmax_workspace_bytes(int B, int Nt);
 int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,

@@ -1,11 +1,11 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "attn_colsum or partial or transformer" > gpurun_out/dev_cs_pytest.log 2>&1; tail -15 gpurun_out/dev_cs_pytest.log
-for f in 1 0; do
-VCR_FUSED_KEY_STAT=$f timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-workloads > gpurun_out/dev_bench_partial_ks$f.json 2>gpurun_out/dev_bench_partial_ks$f.err
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/dev_pytest_gpu.log 2>&1; tail -8 gpurun_out/dev_pytest_gpu.log
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/dev_bench_partial.json 2>gpurun_out/dev_bench_partial.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/dev_bench_partial_ks$f.json"))
-print("fused_key_stat=$f", round(d["value"],1), "pairs/s", d["ms_per_step"], {k:v for k,v in d["kernel_ms_per_step"].items() if "colsum" in k or "gemm_tc" in k})
+d=json.load(open("gpurun_out/dev_bench_partial.json"))
+print("partial", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "whole", {k[:20]:round(v["value"],1) for k,v in d.get("other_workloads",{}).items()})
+k=d["kernel_ms_per_step"]
+for n,v in sorted(k.items(), key=lambda kv:-kv[1])[:14]: print(f"{v:7.3f} {n}")
 PY
-done

@@ -423,6 +423,28 @@ def test_fused_softcorr_vs_oracle_and_row_pass(B, Ns, Nt, D, common):
         assert rel_err(fused, want) < TOL
 
 
+@pytest.mark.parametrize("B,Ns,Nt,D", [(2, 494, 494, 512), (3, 200, 333, 512), (1, 129, 64, 128)])
+def test_fused_copair_argmax_matches_row_pass(B, Ns, Nt, D):
+    """getCopair statistics (argmax_j, max_j P_ij) from the fused tensor-core kernel == the materialised GEMM -> row pass
+    (same products and pd op order, so the integer outcome must be identical), incl. exact ties (duplicated targets)."""
+    from vcr_net_b200 import functional as Fn
+    rs = np.random.RandomState(B + Ns + Nt)
+    base = rs.randn(1, 1, D).astype(np.float32) * 0.5
+    s_tok = (base + 0.05 * rs.randn(B, Ns, D)).astype(np.float32)
+    t_tok = (base + 0.05 * rs.randn(B, Nt, D)).astype(np.float32)
+    t_tok[:, Nt // 2:Nt // 2 + 8] = t_tok[:, 3:11]                   # duplicated targets: exact ties -> lower index
+    s_tok[:, :5] = t_tok[:, 3:8]                                      # sources that coincide with a duplicated target
+    st, tt = cu(s_tok), cu(t_tok)
+    xx, yy = ops.sqnorm_rows(st), ops.sqnorm_rows(tt)
+    bi, bv = ops.softcorr_best_tc(ops.to_operand(st.reshape(B * Ns, D), "h3"), ops.to_operand(tt.reshape(B * Nt, D), "h3"),
+                                  xx, yy, B, Ns, Nt, D)
+    dot, ld = Fn.pair_dots(st, tt)
+    _, ri, rv = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
+    assert torch.equal(bi, ri)
+    assert rel_err(nump(bv), nump(rv)) < 2e-5
+    assert (nump(bi)[:, :5] == np.arange(3, 8)[None]).all()           # the lower of the two equal targets
+
+
 def test_svd_head_vs_golden(net_whole):
     g = load_golden("svd_head")
     R, t = net_whole.svd(cu(g["src"]), cu(g["corr"]))

@@ -51,10 +51,13 @@ __global__ void conv3_kernel(const float* __restrict__ xyz, const float* __restr
 // ---------------------------------------------------------------------------------------------
 // LayerNorm of model/transformer.py:141-144: a*(x-mean)/(std_unbiased+eps)+b.  D % 128 == 0, D <= 1024.
 // ---------------------------------------------------------------------------------------------
-template <int VPL>  // float4 per lane
+// EXTRA: also write the row in operand format (fp16 hi / lo * 2^11 planes) and its squared norm -- the two things the
+// VCP head derives from the Transformer output (to_operand + sqnorm_rows), with the summation order of sqnorm_rows_kernel.
+template <int VPL, bool EXTRA>  // float4 per lane
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
                                  const float* __restrict__ b, float eps, int M, int D,
-                                 const float* __restrict__ res, int ldr, float* __restrict__ out, int ldo) {
+                                 const float* __restrict__ res, int ldr, float* __restrict__ out, int ldo,
+                                 __half* __restrict__ op, int ldop, long long plane, float* __restrict__ sq) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -92,6 +95,23 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
             r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
         }
         o[lane + i * 32] = r;
+        if (EXTRA) v[i] = r;
+    }
+    if (EXTRA) {
+        float n2 = 0.f;
+        __half* oh = op + (size_t)row * ldop;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 r = v[i];
+            n2 += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+            const int c = (lane + i * 32) * 4;
+            *reinterpret_cast<uint2*>(oh + c) = make_uint2(tc::pack_h2(r.x, r.y, 0), tc::pack_h2(r.z, r.w, 0));
+            *reinterpret_cast<uint2*>(oh + plane + c) =
+                make_uint2(tc::pack_h2(tc::lo_part(r.x, 0), tc::lo_part(r.y, 0), 0),
+                           tc::pack_h2(tc::lo_part(r.z, 0), tc::lo_part(r.w, 0), 0));
+        }
+        n2 = warp_sum(n2);
+        if (lane == 0) sq[row] = n2;
     }
 }
 
@@ -547,7 +567,27 @@ VCR_API int vcr_layernorm(const float* x, int ldx, const float* a, const float* 
     const int wpb = 8;
     dim3 g(vcr_cdiv(M, wpb));
     switch (D / 128) {
-#define LN_CASE(V) case V: layernorm_kernel<V><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, residual, ldr, out, ldo); break;
+#define LN_CASE(V) case V: layernorm_kernel<V, false><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, residual, ldr, out, ldo, nullptr, 0, 0, nullptr); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#undef LN_CASE
+    }
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// vcr_layernorm that also emits what the VCP head needs from its output: the operand-format ("h3": fp16 hi, lo * 2^11)
+// copy [2][M][ldop] and the squared row norms sq[M] (bit-identical to vcr_to_operand / vcr_sqnorm_rows of `out`).
+VCR_API int vcr_layernorm_head(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
+                               const float* residual, int ldr, float* out, int ldo, void* op, int ldop,
+                               long long plane_stride, float* sq, cudaStream_t stream) {
+    VCR_REQUIRE(x && a && b && out && op && sq && M > 0);
+    if (D % 128 != 0 || D > 1024 || (ldx & 3) || (ldo & 3) || (residual && (ldr & 3)) || (ldop & 3) || (plane_stride & 3))
+        return VCR_ERR_UNSUPPORTED;
+    const int wpb = 8;
+    dim3 g(vcr_cdiv(M, wpb));
+    __half* oh = reinterpret_cast<__half*>(op);
+    switch (D / 128) {
+#define LN_CASE(V) case V: layernorm_kernel<V, true><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, residual, ldr, out, ldo, oh, ldop, plane_stride, sq); break;
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
     }

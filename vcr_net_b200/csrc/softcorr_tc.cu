@@ -31,10 +31,13 @@ struct SoftcorrParams {
     int B, Ns, Nt, D;
     const float* xx;      // [B*Ns]  |s_i|^2
     const float* yy;      // [B*Nt]  |t_j|^2
-    const float* tgt;     // [B,3,Nt]
-    float* corr;          // [B,3,Ns]
+    const float* tgt;     // [B,3,Nt]           (mode 0)
+    float* corr;          // [B,3,Ns]           (mode 0)
+    int* best_idx;        // [B,Ns] argmax_j     (mode 2: hard correspondences, model/vcrnet_model.py:295-299)
+    float* best_val;      // [B,Ns] max_j P_ij   (mode 2)
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SoftcorrParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -137,8 +140,9 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const bool row_ok = row < p.Ns;
             const float nx = row_ok ? -p.xx[(size_t)b * p.Ns + row] : 0.f;
             const float* yb = p.yy + (size_t)b * p.Nt;
-            const float* tb = p.tgt + (size_t)b * 3 * p.Nt;
+            const float* tb = MODE == 0 ? p.tgt + (size_t)b * 3 * p.Nt : nullptr;
             float m = -INFINITY, s = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+            int mj = 0x7fffffff;                               // MODE 2: arg-max, ties -> lower index
             for (int n_blk = 0; n_blk < tiles_n; ++n_blk, ++tl) {
                 const int a = tl & 1;
                 const uint32_t aph = (tl >> 1) & 1;
@@ -150,9 +154,11 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int cj = col_h + q * 32 + lane;
                     const bool ok = cj < p.Nt;
                     cols[q * 32 + lane] = ok ? yb[cj] : 0.f;
-                    cols[64 + q * 32 + lane] = ok ? tb[cj] : 0.f;
-                    cols[128 + q * 32 + lane] = ok ? tb[p.Nt + cj] : 0.f;
-                    cols[192 + q * 32 + lane] = ok ? tb[2 * p.Nt + cj] : 0.f;
+                    if (MODE == 0) {
+                        cols[64 + q * 32 + lane] = ok ? tb[cj] : 0.f;
+                        cols[128 + q * 32 + lane] = ok ? tb[p.Nt + cj] : 0.f;
+                        cols[192 + q * 32 + lane] = ok ? tb[2 * p.Nt + cj] : 0.f;
+                    }
                 }
                 __syncwarp();
                 tc::mbar_wait(&tfull[a], aph);
@@ -181,20 +187,27 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             if (col0 + j >= p.Nt) pd[j] = -INFINITY;
                     }
                     float cm = pd[0];
+                    int cj = 0;
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) cm = fmaxf(cm, pd[j]);
+                    for (int j = 1; j < 32; ++j) {
+                        if (MODE == 2) { if (pd[j] > cm) { cm = pd[j]; cj = j; } }      // first (lowest) index of the maximum
+                        else cm = fmaxf(cm, pd[j]);
+                    }
                     if (cm > m) {                              // rescale the running sums to the new maximum
                         const float f = __expf(m - cm);        // m = -inf on the first chunk: f = 0
                         s *= f; cx *= f; cy *= f; cz *= f;
                         m = cm;
+                        mj = col0 + cj;                        // columns are visited in increasing order: strict > keeps the lower index
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float e = __expf(pd[j] - m);
                         s += e;
-                        cx = fmaf(e, cols[64 + cc * 32 + j], cx);
-                        cy = fmaf(e, cols[128 + cc * 32 + j], cy);
-                        cz = fmaf(e, cols[192 + cc * 32 + j], cz);
+                        if (MODE == 0) {
+                            cx = fmaf(e, cols[64 + cc * 32 + j], cx);
+                            cy = fmaf(e, cols[128 + cc * 32 + j], cy);
+                            cz = fmaf(e, cols[192 + cc * 32 + j], cz);
+                        }
                     }
                 }
                 tc::tc_fence_before();
@@ -204,7 +217,9 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // ---- combine the two column halves of a row (pair barrier, 64 threads), write corr ----
             if (chalf == 1) {
                 float* x5 = xch + rloc * 5;
-                x5[0] = m; x5[1] = s; x5[2] = cx; x5[3] = cy; x5[4] = cz;
+                x5[0] = m; x5[1] = s;
+                if (MODE == 0) { x5[2] = cx; x5[3] = cy; x5[4] = cz; }
+                else x5[2] = __int_as_float(mj);
             }
             asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
             if (chalf == 0) {
@@ -214,10 +229,18 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float f0 = __expf(m - mt), f1 = __expf(m1 - mt);     // a half without columns has m = -inf: f = 0
                 const float st = s * f0 + x5[1] * f1;
                 if (row_ok) {
-                    float* cb = p.corr + (size_t)b * 3 * p.Ns;
-                    cb[row] = (cx * f0 + x5[2] * f1) / st;
-                    cb[p.Ns + row] = (cy * f0 + x5[3] * f1) / st;
-                    cb[2 * p.Ns + row] = (cz * f0 + x5[4] * f1) / st;
+                    if (MODE == 0) {
+                        float* cb = p.corr + (size_t)b * 3 * p.Ns;
+                        cb[row] = (cx * f0 + x5[2] * f1) / st;
+                        cb[p.Ns + row] = (cy * f0 + x5[3] * f1) / st;
+                        cb[2 * p.Ns + row] = (cz * f0 + x5[4] * f1) / st;
+                    } else {
+                        // equal maxima in the two halves: the lower index wins (the halves interleave 64-column blocks)
+                        const int mj1 = __float_as_int(x5[2]);
+                        const int best = (m1 > m || (m1 == m && mj1 < mj)) ? mj1 : mj;
+                        p.best_idx[(size_t)b * p.Ns + row] = best;
+                        p.best_val[(size_t)b * p.Ns + row] = 1.0f / st;     // exp(0) / sum: the maximum probability
+                    }
                 }
             }
             asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");      // xch reusable for the next item
@@ -233,10 +256,9 @@ softcorr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // S / T: operand-format ("h3": 2 planes, fp16 hi and lo * 2^11) embeddings [2][B*Ns][lds] / [2][B*Nt][ldt];
 // xx / yy: their fp32 squared row norms (vcr_sqnorm_rows); tgt [B,3,Nt]; corr [B,3,Ns].
 // Replaces the matmul + softmax + matmul of model/vcrnet_model.py:337-345 without materialising the score matrix.
-VCR_API int vcr_softcorr_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
-                            const float* xx, const float* yy, const float* tgt, int B, int Ns, int Nt, int D,
-                            float* corr, cudaStream_t stream) {
-    VCR_REQUIRE(S && T && xx && yy && tgt && corr && B > 0 && Ns > 0 && Nt > 0 && D > 0);
+static int softcorr_launch(int mode, const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
+                           const float* xx, const float* yy, const float* tgt, int B, int Ns, int Nt, int D,
+                           float* corr, int* best_idx, float* best_val, cudaStream_t stream) {
     if ((long long)B * (Ns > Nt ? Ns : Nt) > 0x7fffffffLL) return VCR_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmB;
     int rc = vcr_make_operand_tmap(&tmA, S, D, (long long)B * Ns, lds, s_plane, 2, BM);
@@ -245,14 +267,32 @@ VCR_API int vcr_softcorr_tc(const void* S, int lds, long long s_plane, const voi
     if (rc != VCR_OK) return rc;
     SoftcorrParams p;
     p.B = B; p.Ns = Ns; p.Nt = Nt; p.D = D; p.xx = xx; p.yy = yy; p.tgt = tgt; p.corr = corr;
-    if (cudaFuncSetAttribute(softcorr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+    p.best_idx = best_idx; p.best_val = best_val;
+    auto kern = mode == 0 ? softcorr_tc_kernel<0> : softcorr_tc_kernel<2>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
         return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long items = (long long)B * vcr_cdiv(Ns, BM);
     const int grid = (int)(items < sms ? items : sms);
-    softcorr_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
+}
+
+VCR_API int vcr_softcorr_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
+                            const float* xx, const float* yy, const float* tgt, int B, int Ns, int Nt, int D,
+                            float* corr, cudaStream_t stream) {
+    VCR_REQUIRE(S && T && xx && yy && tgt && corr && B > 0 && Ns > 0 && Nt > 0 && D > 0);
+    return softcorr_launch(0, S, lds, s_plane, T, ldt, t_plane, xx, yy, tgt, B, Ns, Nt, D, corr, nullptr, nullptr, stream);
+}
+
+// getCopair (model/vcrnet_model.py:264-332), same fused kernel: best_idx[B,Ns] = argmax_j pd_ij (ties -> lower j),
+// best_val[B,Ns] = max_j softmax_j(pd_ij).
+VCR_API int vcr_softcorr_best_tc(const void* S, int lds, long long s_plane, const void* T, int ldt, long long t_plane,
+                                 const float* xx, const float* yy, int B, int Ns, int Nt, int D,
+                                 int* best_idx, float* best_val, cudaStream_t stream) {
+    VCR_REQUIRE(S && T && xx && yy && best_idx && best_val && B > 0 && Ns > 0 && Nt > 0 && D > 0);
+    return softcorr_launch(2, S, lds, s_plane, T, ldt, t_plane, xx, yy, nullptr, B, Ns, Nt, D, nullptr, best_idx, best_val, stream);
 }

@@ -564,7 +564,15 @@ def _ln_op(norm, x, mode):
     return ops.layernorm_operand(x, norm.a_2, norm.b_2, norm.eps, mode)
 
 
-def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False):
+class HeadPre:
+    """What the VCP head derives from a Transformer output: its "h3" operand copy and squared row norms, written by the
+    final LayerNorm kernel (vcr_layernorm_head) instead of separate to_operand / sqnorm_rows passes."""
+
+    def __init__(self, op, sq):
+        self.op, self.sq = op, sq
+
+
+def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False, want_head=False):
     """swap_mem: decoder batch item b attends to the encoder output of item (b + B/2) mod B -- the two directions of
     Transformer.forward run as one batch [src; tgt] without building the swapped copy [tgt; src]: only the encoder's
     final LayerNorm writes its two halves exchanged."""
@@ -586,10 +594,13 @@ def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False):
         y = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, y, mode), None, B, Nt, Nt, y, mode)
         y = mha_tc(layer.src_attn, _ln_op(layer.sublayer[1].norm, y, mode), mem, B, Nt, Ns, y, mode)
         y = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[2].norm, y, mode), B * Nt, y, mode)
+    if want_head:
+        nrm = model.decoder.norm
+        return ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=final_residual)
     return _ln(model.decoder.norm, y, residual=final_residual)
 
 
-def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_input=False):
+def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_input=False, want_head=False):
     """Transformer.forward on tokens (model/transformer.py:264-272).  The two directions
     (model(src,tgt) -> tgt_p and model(tgt,src) -> src_p) share weights and are independent, so
     they run as ONE batch of 2B.  Returns (src_p, tgt_p) tokens; with ``add_input`` the
@@ -605,21 +616,27 @@ def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_inp
             enc_in = torch.cat([src_tok, tgt_tok], dim=0)
         if config.precision != "fp32":
             enc_in = enc_in.contiguous()
-            out = encoder_decoder_tc(tr.model, enc_in, enc_in, enc_in if add_input else None, config.precision, swap_mem=True)
+            out = encoder_decoder_tc(tr.model, enc_in, enc_in, enc_in if add_input else None, config.precision, swap_mem=True,
+                                     want_head=want_head)
+            if want_head:
+                out, op, sq = out
+                n = out.shape[1]
+                pre = (HeadPre(op.rows_view(0, B * n), sq[:B]), HeadPre(op.rows_view(B * n, B * n), sq[B:]))
+                return out[:B], out[B:], pre
             return out[:B], out[B:]
         dec_in = torch.cat([tgt_tok, src_tok], dim=0)
         out = encoder_decoder_tok(tr.model, enc_in, dec_in, final_residual=dec_in if add_input else None)
-        return out[B:], out[:B]
+        return (out[B:], out[:B], None) if want_head else (out[B:], out[:B])
     tgt_p = encoder_decoder_tok(tr.model, src_tok, tgt_tok, final_residual=tgt_tok if add_input else None)
     src_p = encoder_decoder_tok(tr.model, tgt_tok, src_tok, final_residual=src_tok if add_input else None)
-    return src_p, tgt_p
+    return (src_p, tgt_p, None) if want_head else (src_p, tgt_p)
 
 
 # --------------------------------------------------------------------------------------------------
 # VCP head
 # --------------------------------------------------------------------------------------------------
 
-def pair_dots(src_tok, tgt_tok, alpha=1.0):
+def pair_dots(src_tok, tgt_tok, alpha=1.0, pre=None):
     """dot[b,i,j] = alpha * s_i . t_j (the matmul of model/vcrnet_model.py:337): fp32 SIMT or 3-term tensor cores.
     The throughput modes keep the 3-term split here: these logits cancel catastrophically
     (|f|^2 ~ 500 against gaps < 1), SURVEY.md section 7 hard part 2."""
@@ -632,21 +649,27 @@ def pair_dots(src_tok, tgt_tok, alpha=1.0):
     Nt = tgt_tok.shape[1]
     ld = (Nt + 3) // 4 * 4
     dot = torch.empty((B, Ns, ld), dtype=_F32, device=src_tok.device)
-    ops.gemm_tc(ops.to_operand(src_tok, "h3"), ops.to_operand(tgt_tok, "h3"), Ns, Nt, D, nbo=B,
+    s_op = pre[0].op if pre is not None else ops.to_operand(src_tok, "h3")
+    t_op = pre[1].op if pre is not None else ops.to_operand(tgt_tok, "h3")
+    ops.gemm_tc(s_op, t_op, Ns, Nt, D, nbo=B,
                 a_off=(Ns, 0, 0, 0), b_off=(Nt, 0, 0, 0), alpha=alpha, c=dot, c_strides=(Ns * ld, 0))
     return dot, ld
 
 
-def vcp_whole(src_tok, tgt_tok, tgt_xyz):
-    """getCopairALL (model/vcrnet_model.py:334-347): src_corr [B,3,N]."""
+def vcp_whole(src_tok, tgt_tok, tgt_xyz, pre=None):
+    """getCopairALL (model/vcrnet_model.py:334-347): src_corr [B,3,N].  pre: (HeadPre src, HeadPre tgt) from the final
+    LayerNorm of the Transformer (operand copies + squared norms already in HBM)."""
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
-    xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
+    if pre is not None and config.precision == "fp32":
+        pre = None
+    xx, yy = (pre[0].sq, pre[1].sq) if pre is not None else (ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok))
     if config.precision != "fp32" and config.fused_softcorr:
         # one kernel: 3-term tcgen05 products + online softmax + weighted sum of the target points in the epilogue
-        return ops.softcorr_tc(ops.to_operand(src_tok.reshape(B * Ns, D), "h3"), ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3"),
-                               xx, yy, tgt_xyz, B, Ns, Nt, D)
-    dot, ld = pair_dots(src_tok, tgt_tok)
+        s_op = pre[0].op if pre is not None else ops.to_operand(src_tok.reshape(B * Ns, D), "h3")
+        t_op = pre[1].op if pre is not None else ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3")
+        return ops.softcorr_tc(s_op, t_op, xx, yy, tgt_xyz, B, Ns, Nt, D)
+    dot, ld = pair_dots(src_tok, tgt_tok, pre=pre)
     corr, _, _ = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, tgt=tgt_xyz.contiguous(), mode=0)
     return corr
 
@@ -671,15 +694,17 @@ def vcp_att(m, src_tok, tgt_tok, tgt_xyz):
     return vcp_whole(q, k, tgt_xyz)
 
 
-def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):
+def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2, pre=None):
     """selectCom (model/vcrnet_model.py:190-262) without the unused *_remain host round trips."""
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
     srcK = int(Ns * 0.84 * overlap2)
     tgtK = int(Nt * 0.84 * overlap2)
     src_tok, tgt_tok = src_tok.contiguous(), tgt_tok.contiguous()
-    dot, ld = pair_dots(src_tok, tgt_tok)
-    xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
+    if pre is not None and config.precision == "fp32":
+        pre = None
+    dot, ld = pair_dots(src_tok, tgt_tok, pre=pre)
+    xx, yy = (pre[0].sq, pre[1].sq) if pre is not None else (ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok))
     pd = ops.negdist_(dot, ld, Ns, Nt, xx, yy)                        # scores (:213-214)
     row_stat = ops.rowsum_colsoftmax(pd, ld, Ns, Nt)                  # softmax over dim=1, sum dim=2 (:243-244)
     P = ops.softmax_rows_(pd.view(B * Ns, ld)[:, :Nt])                # softmax over dim=2 (:221)
@@ -696,9 +721,13 @@ def vcp_copair(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):
     B, Ns, D = src_tok.shape
     Nt = tgt_tok.shape[1]
     srcK = int(Ns * 0.52 * overlap2)
-    dot, ld = pair_dots(src_tok, tgt_tok)
     xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
-    _, best_i, best_v = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
+    if config.precision != "fp32" and config.fused_softcorr:
+        best_i, best_v = ops.softcorr_best_tc(ops.to_operand(src_tok.reshape(B * Ns, D), "h3"),
+                                              ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3"), xx, yy, B, Ns, Nt, D)
+    else:
+        dot, ld = pair_dots(src_tok, tgt_tok)
+        _, best_i, best_v = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
     keep, _ = ops.topk_select(best_v, srcK)                            # [B,srcK] sorted by confidence
     src_k, corr_k = ops.copair_gather(src_xyz, tgt_xyz, keep, best_i)
     return src_k, corr_k, keep, best_i

@@ -154,8 +154,10 @@ class Transformer(nn.Module):
                                             self.N),
                                     nn.Sequential(), nn.Sequential(), nn.Sequential())
 
-    def forward_tokens(self, src_tok, tgt_tok, add_input=False):
-        return Fn.transformer_tokens(self, src_tok, tgt_tok, add_input=add_input)
+    def forward_tokens(self, src_tok, tgt_tok, add_input=False, want_head=False):
+        """want_head: also return (HeadPre src, HeadPre tgt) -- operand copies + squared norms of the outputs written by the
+        final LayerNorm kernel -- or None when the path does not produce them."""
+        return Fn.transformer_tokens(self, src_tok, tgt_tok, add_input=add_input, want_head=want_head)
 
     def forward(self, *input):
         src_tok = ops.transpose_batched(input[0])

@@ -105,12 +105,12 @@ class VcpTopK(nn.Module):
         self.partial = args.partial
         self.overlap2 = float(args.overlap2)
 
-    def forward_tokens(self, src_tok, tgt_tok, src, tgt):
+    def forward_tokens(self, src_tok, tgt_tok, src, tgt, pre=None):
         if self.partial:
-            so, seo, to, teo, _, _ = Fn.vcp_select(src, src_tok, tgt, tgt_tok, self.overlap2)
+            so, seo, to, teo, _, _ = Fn.vcp_select(src, src_tok, tgt, tgt_tok, self.overlap2, pre=pre)
             s, c, _, _ = Fn.vcp_copair(so, seo, to, teo, self.overlap2)
             return s, c
-        return src, Fn.vcp_whole(src_tok.contiguous(), tgt_tok.contiguous(), tgt)
+        return src, Fn.vcp_whole(src_tok.contiguous(), tgt_tok.contiguous(), tgt, pre=pre)
 
     def forward(self, *input):
         src_tok = ops.transpose_batched(input[0])
@@ -226,13 +226,19 @@ class VCRNet(nn.Module):
             src_tok, tgt_tok = self.emb_nn.forward_tokens(src), self.emb_nn.forward_tokens(tgt)
         if stages is not None:
             stages.update(src_emb0=src_tok, tgt_emb0=tgt_tok)
+        pre = None
         if isinstance(self.pointer, Transformer):
-            src_tok, tgt_tok = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True)   # :503-505
+            if isinstance(self.head, VcpTopK):     # the final LayerNorm also writes what the head derives from its output
+                src_tok, tgt_tok, pre = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True, want_head=True)
+            else:
+                src_tok, tgt_tok = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True)   # :503-505
         if stages is not None:
             stages.update(src_emb=src_tok, tgt_emb=tgt_tok)
-        srcK, src_corrK = self.head.forward_tokens(src_tok, tgt_tok, src, tgt)                  # :507
+        hk = {"pre": pre} if pre is not None else {}
+        srcK, src_corrK = self.head.forward_tokens(src_tok, tgt_tok, src, tgt, **hk)            # :507
         R_ab, t_ab, R_ba, t_ba = ops.svd_head(srcK, src_corrK)                                  # :509-516
         if self.cycle:
-            srcK_ba, corrK_ba = self.head.forward_tokens(tgt_tok, src_tok, tgt, src)
+            hk = {"pre": (pre[1], pre[0])} if pre is not None else {}
+            srcK_ba, corrK_ba = self.head.forward_tokens(tgt_tok, src_tok, tgt, src, **hk)
             R_ba, t_ba, _, _ = ops.svd_head(srcK_ba, corrK_ba)
         return srcK, src_corrK, R_ab, t_ab, R_ba, t_ba

@@ -473,6 +473,23 @@ def layernorm(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e
     return out
 
 
+def layernorm_head(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, residual=None):
+    """layernorm(x) (+ residual) -> (out fp32, its "h3" Operand copy, its squared row norms), one kernel."""
+    _chk(x, "x")
+    M, D, ldx = _rows(x)
+    out = torch.empty(x.shape, dtype=_F32, device=x.device)
+    op = Operand.empty(M, D, "h3", x.device)
+    sq = torch.empty(x.shape[:-1], dtype=_F32, device=x.device)
+    ldr = 0
+    if residual is not None:
+        _, _, ldr = _rows(residual)
+    L = lib()
+    L.check(L.vcr_layernorm_head(x.data_ptr(), ldx, a.data_ptr(), b.data_ptr(), float(eps), M, D,
+                                 residual.data_ptr() if residual is not None else None, ldr, out.data_ptr(), D,
+                                 op.ptr, op.ld, op.plane_stride, sq.data_ptr(), _stream(x)), "vcr_layernorm_head")
+    return out, op, sq
+
+
 def softmax_rows_(S: torch.Tensor, keep: torch.Tensor | None = None, rows_per_batch: int = 0):
     rows, n, ld = _rows(S)
     L = lib()
@@ -595,6 +612,19 @@ def softcorr_tc(s_op: "Operand", t_op: "Operand", xx, yy, tgt_xyz: torch.Tensor,
                               xx.data_ptr(), yy.data_ptr(), tgt_xyz.data_ptr(), B, Ns, Nt, D, corr.data_ptr(),
                               _stream(tgt_xyz)), "vcr_softcorr_tc")
     return corr
+
+
+def softcorr_best_tc(s_op: "Operand", t_op: "Operand", xx, yy, B: int, Ns: int, Nt: int, D: int):
+    """Fused getCopair statistics on tensor cores: (argmax_j pd_ij int32 [B,Ns], max_j softmax_j(pd_ij) [B,Ns])."""
+    assert s_op.mode == "h3" and t_op.mode == "h3" and s_op.rows == B * Ns and t_op.rows == B * Nt
+    dev = xx.device
+    best_i = torch.empty((B, Ns), dtype=torch.int32, device=dev)
+    best_v = torch.empty((B, Ns), dtype=_F32, device=dev)
+    L = lib()
+    L.check(L.vcr_softcorr_best_tc(s_op.ptr, s_op.ld, s_op.plane_stride, t_op.ptr, t_op.ld, t_op.plane_stride,
+                                   xx.data_ptr(), yy.data_ptr(), B, Ns, Nt, D, best_i.data_ptr(), best_v.data_ptr(),
+                                   _stream(xx)), "vcr_softcorr_best_tc")
+    return best_i, best_v
 
 
 def negdist_(dot, ld, Ns, Nt, xx, yy):
