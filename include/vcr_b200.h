@@ -104,6 +104,9 @@ int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const void* K, 
                       const void* VT, int ldv, long long v_plane, int B, int H, int Nq, int Nk, int dk,
                       int mode, float scale, const uint8_t* keep, void* O, int ldo, long long o_plane,
                       float* lse, cudaStream_t stream);
+/* Process-wide switch (default 0): run the mode-0 GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of
+ * SMs, each CTA staging half of the B tile).  Same results; returns the previous setting. */
+int vcr_set_gemm_pair(int on);
 int vcr_to_operand(const float* x, int ld, long long rows, int cols, void* out, int ldo, long long plane_stride,
                    int planes, int bf16, cudaStream_t stream);
 

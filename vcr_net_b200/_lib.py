@@ -98,4 +98,7 @@ def lib() -> _Lib:
     global _instance
     if _instance is None:
         _instance = _Lib()
+        from . import config
+        if config.gemm_pair:
+            _instance.vcr_set_gemm_pair(1)
     return _instance

@@ -53,3 +53,8 @@ def set_precision(p: str):
     if p not in VALID:
         raise ValueError(f"precision must be one of {VALID}")
     precision = p
+
+
+# 3-term ("h3") GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of SMs; csrc/gemm_tc.cu).  Same results
+# bit for bit; applied to the library when it is loaded (ops.lib()) and switchable with ops.set_gemm_pair().
+gemm_pair = os.environ.get("VCR_GEMM_PAIR", "0") == "1"

@@ -45,11 +45,15 @@ struct TcGemmParams {
     int out_bf16;        // operand-format outputs are bf16 instead of fp16 (bf16 throughput mode)
 };
 
-template <int NTERMS>
+// CTAS = 2: CTA pairs (cta_group::2, 256 x 128 tile per pair): a CTA stages its 128 A rows and HALF of the B tile
+// (64 rows) per k-block -- 48 KB instead of 64 KB in the 3-term mode, so 4 stages fit and the L2 -> SM operand traffic
+// per MMA drops by a quarter.
+template <int NTERMS, int CTAS = 1>
 struct Cfg {
     static constexpr int PLANES = NTERMS == 3 ? 2 : 1;
-    static constexpr int STAGE_BYTES = 2 * PLANES * TILE_BYTES;
-    static constexpr int NSTAGES = NTERMS == 3 ? 3 : 6;
+    static constexpr int B_TILE_BYTES = TILE_BYTES / CTAS;
+    static constexpr int STAGE_BYTES = PLANES * (TILE_BYTES + B_TILE_BYTES);
+    static constexpr int NSTAGES = CTAS == 2 ? 4 : (NTERMS == 3 ? 3 : 6);
     static constexpr int ACC_COLS = NTERMS == 3 ? 2 * BN : BN;      // D0 | D1
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                  // double-buffered
     static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
@@ -59,10 +63,10 @@ struct Cfg {
 using tc::pack_h2;
 using tc::lo_part;
 
-template <int NTERMS, int FMT>
+template <int NTERMS, int FMT, int CTAS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
-    using C_ = Cfg<NTERMS>;
+    using C_ = Cfg<NTERMS, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::NSTAGES * C_::STAGE_BYTES);
@@ -74,10 +78,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* stage_buf = reinterpret_cast<float*>(smem + C_::NSTAGES * C_::STAGE_BYTES + 256);   // [EPI_WARPS][32][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    // a scheduling unit is a 128-row tile (CTAS = 1) or a 256-row tile pair (CTAS = 2: this CTA takes rows rank*128..)
+    const int tiles_m = (p.M + CTAS * BM - 1) / (CTAS * BM), tiles_n = (p.N + BN - 1) / BN;
     const int tiles_per_z = tiles_m * tiles_n;
     const long long total_tiles = (long long)tiles_per_z * p.nb_outer * p.nb_inner;
     const int nkb = (p.K + BK - 1) / BK;
+    const int rank = CTAS == 2 ? (int)tc::cluster_ctarank() : 0;
+    const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -85,15 +92,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C_::NSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS * 32 * CTAS); }
         tc::fence_barrier_init();
     }
     if (warp == 2) {
-        tc::tmem_alloc(tmem_slot, C_::TMEM_COLS);
-        tc::tmem_relinquish();
+        if (CTAS == 2) { tc::tmem_alloc_2sm(tmem_slot, C_::TMEM_COLS); tc::tmem_relinquish_2sm(); }
+        else { tc::tmem_alloc(tmem_slot, C_::TMEM_COLS); tc::tmem_relinquish(); }
     }
     tc::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) tc::cluster_sync_all();      // the peer's barriers exist before anything signals them
+    else __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -101,34 +109,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (tc::elect_one()) {
             int s = 0; uint32_t ph = 0;
-            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (long long t = unit0; t < total_tiles; t += unit_step) {
                 const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
-                const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+                const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = r % tiles_n;
                 const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
                 const int a_row = (int)(zo * p.a_row_o + zi * p.a_row_i) + m_blk * BM;
-                const int b_row = (int)(zo * p.b_row_o + zi * p.b_row_i) + n_blk * BN;
+                const int b_row = (int)(zo * p.b_row_o + zi * p.b_row_i) + n_blk * BN + rank * (BN / CTAS);
                 const int a_col = zo * p.a_col_o + zi * p.a_col_i;
                 const int b_col = zo * p.b_col_o + zi * p.b_col_i;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc::mbar_wait(&empty[s], ph ^ 1);
-                    tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
                     uint8_t* st = smem + s * C_::STAGE_BYTES;
+                    if (CTAS == 2) {
+                        // the leader's barrier collects the bytes of both CTAs; only the leader arms it
+                        if (rank == 0) tc::mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);
 #pragma unroll
-                    for (int pl = 0; pl < C_::PLANES; ++pl) {
-                        tc::tma_load_3d(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
-                        tc::tma_load_3d(st + (C_::PLANES + pl) * TILE_BYTES, &tmB, &full[s], b_col + kb * BK, b_row, pl);
+                        for (int pl = 0; pl < C_::PLANES; ++pl) {
+                            tc::tma_load_3d_2sm(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
+                            tc::tma_load_3d_2sm(st + C_::PLANES * TILE_BYTES + pl * C_::B_TILE_BYTES, &tmB, &full[s],
+                                                b_col + kb * BK, b_row, pl);
+                        }
+                    } else {
+                        tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+#pragma unroll
+                        for (int pl = 0; pl < C_::PLANES; ++pl) {
+                            tc::tma_load_3d(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
+                            tc::tma_load_3d(st + (C_::PLANES + pl) * TILE_BYTES, &tmB, &full[s], b_col + kb * BK, b_row, pl);
+                        }
                     }
                     if (++s == C_::NSTAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (the leader CTA of a pair) =====================
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc(BM, BN, FMT);
+            constexpr uint32_t idesc = tc::umma_idesc(CTAS * BM, BN, FMT);
             int s = 0; uint32_t ph = 0;
             int it = 0;
-            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            for (long long t = unit0; t < total_tiles; t += unit_step, ++it) {
                 const int a = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 tc::mbar_wait(&tempty[a], aph ^ 1);
@@ -145,18 +164,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint32_t acc = (kb | kk) != 0;
                         const uint64_t adv = (uint64_t)(kk * 32 >> 4);      // 16 elements = 32 B along K
-                        tc::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
-                        if (NTERMS == 3) {
-                            const uint64_t a_lo = tc::umma_desc_k_sw128(st + TILE_BYTES);
-                            const uint64_t b_lo = tc::umma_desc_k_sw128(st + 3 * TILE_BYTES);
-                            tc::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
-                            tc::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1);
+                        if (CTAS == 2) {
+                            tc::umma_f16_2sm(d0, a_hi + adv, b_hi + adv, idesc, acc);
+                            if (NTERMS == 3) {
+                                const uint64_t a_lo = tc::umma_desc_k_sw128(st + TILE_BYTES);
+                                const uint64_t b_lo = tc::umma_desc_k_sw128(st + 2 * TILE_BYTES + C_::B_TILE_BYTES);
+                                tc::umma_f16_2sm(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                                tc::umma_f16_2sm(d1, a_lo + adv, b_hi + adv, idesc, 1);
+                            }
+                        } else {
+                            tc::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
+                            if (NTERMS == 3) {
+                                const uint64_t a_lo = tc::umma_desc_k_sw128(st + TILE_BYTES);
+                                const uint64_t b_lo = tc::umma_desc_k_sw128(st + 3 * TILE_BYTES);
+                                tc::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                                tc::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1);
+                            }
                         }
                     }
-                    tc::umma_commit(&empty[s]);               // smem slot free once these MMAs retire
+                    if (CTAS == 2) tc::umma_commit_2sm(&empty[s]);   // frees the stage in both CTAs
+                    else tc::umma_commit(&empty[s]);               // smem slot free once these MMAs retire
                     if (++s == C_::NSTAGES) { s = 0; ph ^= 1; }
                 }
-                tc::umma_commit(&tfull[a]);                    // accumulator ready for the epilogue
+                if (CTAS == 2) tc::umma_commit_2sm(&tfull[a]);      // both CTAs' epilogues
+                else tc::umma_commit(&tfull[a]);                    // accumulator ready for the epilogue
             }
         }
     } else if (warp >= 4) {
@@ -180,9 +211,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* stg = stage_buf + (warp - 4) * (32 * 32);
         const int c4 = lane & 7, rsub = lane >> 3;
         int it = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (long long t = unit0; t < total_tiles; t += unit_step, ++it) {
             const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
-            const int m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
+            const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = r % tiles_n;
             const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -343,12 +374,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (!waited) { tc::mbar_wait(&tfull[a], aph); tc::tc_fence_after(); }
             tc::tc_fence_before();
-            tc::mbar_arrive(&tempty[a]);
+            if (CTAS == 2) tc::mbar_arrive_cluster(&tempty[a], 0);   // the leader's MMA issuer waits for both CTAs
+            else tc::mbar_arrive(&tempty[a]);
         }
     }
     tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+    if (CTAS == 2) {
+        tc::cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while the pair is still working
+        if (warp == 2) tc::tmem_dealloc_2sm(tmem_base, C_::TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+    }
 }
 
 // fp32 [rows, cols] (ld) -> operand format planes (hi, and lo*2^11 when planes == 2)
@@ -370,10 +407,44 @@ __global__ void to_operand_kernel(const float* __restrict__ x, int ld, long long
     }
 }
 
+// CTA-pair launch (cta_group::2): cluster (2,1,1), one pair per TPC.  Returns VCR_ERR_UNSUPPORTED when the device cannot
+// co-schedule pairs (the caller then uses the single-CTA kernel).
+int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams& p, cudaStream_t stream) {
+    using C_ = Cfg<3, 2>;
+    auto kern = gemm_tc_kernel<3, 0, 2>;
+    static int max_pairs = -1;             // idempotent, benign race
+    if (max_pairs < 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
+            return VCR_ERR_LAUNCH;
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(2, 1, 1); q.blockDim = dim3(NTHREADS, 1, 1); q.dynamicSmemBytes = C_::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        q.attrs = at; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        max_pairs = n;
+    }
+    if (max_pairs < 1) return VCR_ERR_UNSUPPORTED;
+    const long long units = (long long)vcr_cdiv(p.M, 2 * BM) * vcr_cdiv(p.N, BN) * p.nb_outer * p.nb_inner;
+    const int pairs = (int)(units < max_pairs ? units : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1); cfg.blockDim = dim3(NTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = C_::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p) != cudaSuccess) { cudaGetLastError(); return VCR_ERR_LAUNCH; }
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
 template <int NTERMS, int FMT>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams& p, cudaStream_t stream) {
     using C_ = Cfg<NTERMS>;
-    auto kern = gemm_tc_kernel<NTERMS, FMT>;
+    auto kern = gemm_tc_kernel<NTERMS, FMT, 1>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
         return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
@@ -387,6 +458,8 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams
 }
 
 }  // namespace
+
+static int g_vcr_gemm_pair = 0;
 
 vcr_tmap_encode_fn vcr_get_tmap_encoder() {
     static vcr_tmap_encode_fn fn = nullptr;
@@ -452,9 +525,24 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
     p.h_split = H ? (HT ? h_split : N) : 0;
     p.HT = reinterpret_cast<__half*>(HT); p.ldt = ldt; p.t_plane = t_plane; p.t_so = t_so; p.t_si = t_si;
     p.out_planes = out_planes; p.out_bf16 = mode == 2;
+    if (mode == 0 && g_vcr_gemm_pair) {
+        // CTA pairs (cta_group::2): each CTA of a pair stages half of the B tile (box of 64 rows)
+        CUtensorMap tmB2;
+        rc = vcr_make_operand_tmap(&tmB2, B, b_cols_total, b_rows_total, ldb, b_plane, planes, BN / 2);
+        if (rc != VCR_OK) return rc;
+        rc = launch_tc_pair(tmA, tmB2, p, stream);
+        if (rc != VCR_ERR_UNSUPPORTED) return rc;
+    }
     if (mode == 0) return launch_tc<3, 0>(tmA, tmB, p, stream);
     if (mode == 1) return launch_tc<1, 0>(tmA, tmB, p, stream);
     return launch_tc<1, 1>(tmA, tmB, p, stream);
+}
+
+// Process-wide switch: run the 3-term ("h3") GEMMs on CTA pairs (cta_group::2).  Returns the previous setting.
+VCR_API int vcr_set_gemm_pair(int on) {
+    const int old = g_vcr_gemm_pair;
+    g_vcr_gemm_pair = on ? 1 : 0;
+    return old;
 }
 
 // fp32 [rows, cols] (row stride ld) -> operand format [planes][rows][ldo] (fp16, or bf16 when bf16 != 0)

@@ -236,6 +236,11 @@ def gemm_tc(a: Operand, b: Operand, M, N, K, *, nbo=1, nbi=1,
         outp.planes if outp is not None else 1, _stream(a.buf)), "vcr_gemm_tc")
 
 
+def set_gemm_pair(on: bool) -> bool:
+    """Run the h3 GEMMs on CTA pairs (tcgen05 cta_group::2); returns the previous setting.  Results are bit-identical."""
+    return bool(lib().vcr_set_gemm_pair(int(bool(on))))
+
+
 def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, Nk, dk, scale, keep=None, lse=None):
     """softmax(Q K^T * scale) V per (batch, head) on tensor cores, nothing of size Nq x Nk touches HBM."""
     L = lib()
