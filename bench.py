@@ -176,7 +176,7 @@ def gemm_flops(args):
     return 2.0 * M * N * K * nbo * nbi
 
 
-def measure(a, cfg, rank, world, dev, local_rank, steps, warmup, profile=True):
+def measure(a, cfg, rank, world, dev, local_rank, steps, warmup, profile=True, graph=False):
     """Time `steps` steps of one workload on this rank's GPU.  Returns per-rank sums (ms) and the per-call profile."""
     import torch
     import torch.distributed as dist
@@ -206,7 +206,15 @@ def measure(a, cfg, rank, world, dev, local_rank, steps, warmup, profile=True):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     stream = torch.cuda.current_stream()
 
+    reg = None
+    if graph:          # the whole --iter loop as one CUDA graph (vcr_net_b200/graph.py); same kernels, one launch
+        from vcr_net_b200.graph import GraphedRegistration
+        reg = GraphedRegistration(net, batch=B, num_points=int(devb[0][0].shape[2]), iter=cfg["iters"],
+                                  num_points_tgt=int(devb[0][1].shape[2]))
+
     def run(s, t):
+        if reg is not None:
+            return reg(s, t)
         if train:
             net.zero_grad(set_to_none=True)
             out = net(s, t)
@@ -341,6 +349,16 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
                                 "e2e": r2["B"] * steps2 * world / (e2 / 1e3), "batch_per_gpu": r2["B"],
                                 "ms_per_step": m2 / steps2, "steps": steps2}}
     # labelled variant: loop-invariant target embedding computed once per vcrnetIter call (bit-identical outputs)
+    graphed = None
+    if not cfg.get("train") and not a.no_other_workloads:
+        steps4 = max(5, a.steps // 2)
+        r4 = measure(a, cfg, rank, world, dev, local_rank, steps4, 3, profile=False, graph=True)
+        m4, e4 = reduce_max(world, dev, r4["ms_total"], r4["ms_e2e"])
+        graphed = {"value": r4["B"] * steps4 * world / (m4 / 1e3), "e2e": r4["B"] * steps4 * world / (e4 / 1e3),
+                   "unit": "pairs/s", "steps": steps4,
+                   "note": "vcr_net_b200.graph.GraphedRegistration: the same vcrnetIter loop captured once and replayed as "
+                           "ONE CUDA graph (bit-identical outputs; inputs copied into the graph's static buffers inside "
+                           "the timed region); NOT the headline, which goes through the reference-facing module API"}
     reuse = None
     if cfg["iters"] > 1 and not cfg.get("train") and not a.no_other_workloads:
         vcfg.reuse_target_embedding = True
@@ -421,6 +439,8 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         line["other_workloads"] = other
     if reuse:
         line["variant_reuse_target_embedding"] = reuse
+    if graphed:
+        line["variant_cuda_graph"] = graphed
     if not a.no_cpu_baseline and not cfg.get("train"):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, a.cpu_sample_pairs)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",

@@ -104,9 +104,13 @@ int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const void* K, 
                       const void* VT, int ldv, long long v_plane, int B, int H, int Nq, int Nk, int dk,
                       int mode, float scale, const uint8_t* keep, void* O, int ldo, long long o_plane,
                       float* lse, cudaStream_t stream);
-/* Process-wide switch (default 0): run the mode-0 GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of
- * SMs, each CTA staging half of the B tile).  Same results; returns the previous setting. */
+/* Process-wide policy for the mode-0 GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of SMs, each
+ * CTA staging half of the B tile): 0 never, 1 always, 2 auto (default: pairs except for the residual epilogue at
+ * K < 1024).  Same results bit for bit; returns the previous setting. */
 int vcr_set_gemm_pair(int on);
+/* Policy 3: clusters of two pairs working on the same 256 rows, the A tile multicast between them.  This returns how many
+ * such 4-CTA clusters the device co-schedules (0: unsupported; policy 3 then behaves like 1). */
+int vcr_gemm_quad_clusters(void);
 int vcr_to_operand(const float* x, int ld, long long rows, int cols, void* out, int ldo, long long plane_stride,
                    int planes, int bf16, cudaStream_t stream);
 

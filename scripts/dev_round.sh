@@ -1,3 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 560 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -q -k "not 4096 and not cfg4 and not 2048 and not full_size" > gpurun_out/dev_sanitizer_full.log 2>&1; echo "rc=$?" >> gpurun_out/dev_sanitizer_full.log; tail -25 gpurun_out/dev_sanitizer_full.log
+timeout -s KILL 120 python scripts/pair_diag.py > gpurun_out/dev_pair_diag4.txt 2>&1; echo "rc=$?" >> gpurun_out/dev_pair_diag4.txt
+tail -40 gpurun_out/dev_pair_diag4.txt
+nvidia-smi --query-gpu=name,temperature.gpu --format=csv

@@ -928,3 +928,61 @@ def test_gemm_f32_ragged_k():
     v = rs.randn(K, 64).astype(np.float32)                                                      # [K, N] layout
     got = nump(ops.gemm(cu(a)[:, :K], cu(v), b_layout=1))
     assert rel_err(got, a[:, :K].astype(np.float64) @ v.astype(np.float64)) < 1e-5
+
+
+# ---------------------------------------------------------------- CUDA-graph replay, CTA-pair GEMM ---------------------
+@pytest.mark.parametrize("partial,B,N,it", [(False, 2, 512, 1), (True, 1, 1024, 3)])
+def test_graphed_registration_is_bit_identical(net_whole, net_partial, partial, B, N, it):
+    """vcr_net_b200.graph.GraphedRegistration: the whole --iter loop as ONE CUDA graph (the path has no host sync, no
+    data-dependent shape, no hidden allocation); replay on new inputs == eager path, bit for bit."""
+    from vcr_net_b200.graph import GraphedRegistration
+    net = net_partial if partial else net_whole
+    p = synth.make_pairs(2 * B, N, partial=partial, first_item=61)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    reg = GraphedRegistration(net, batch=B, num_points=src.shape[2], iter=it)
+    for lo in (0, B):                                             # two different batches through the same graph
+        with torch.no_grad():
+            eager = V.vcrnetIter(net, src[lo:lo + B], tgt[lo:lo + B], iter=it)
+        got = reg(src[lo:lo + B], tgt[lo:lo + B])
+        for a, b in zip(eager, got):
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        reg(src[:B, :, :100], tgt[:B])
+
+
+@pytest.mark.parametrize("M,N,K,nbo", [(256, 128, 64, 1), (300, 200, 72, 1), (494, 494, 512, 3), (1000, 130, 520, 1),
+                                       (64, 64, 64, 5), (2048, 1536, 512, 2)])
+def test_gemm_cta_pair_is_bit_identical(M, N, K, nbo):
+    """cta_group::2 variant of the h3 GEMM (256 x 128 tile per SM pair, B tile split across the pair): same bits as the
+    single-CTA kernel for fp32 / operand-format / residual / activation epilogues, ragged M, N, K and batches."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(nbo * M, K, generator=g).to(DEV)
+    w = torch.randn(N, K, generator=g).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    R = torch.randn(nbo * M, N, generator=g).to(DEV)
+    A, Bm = ops.to_operand(a, "h3"), ops.to_operand(w, "h3")
+
+    def run(pair):
+        old = ops.set_gemm_pair(pair)
+        try:
+            kw = dict(bias=bias, act=1, slope=0.2)
+            if nbo > 1:
+                kw.update(nbo=nbo, a_off=(M, 0, 0, 0))
+            c = torch.full((nbo * M, N), float("nan"), device=DEV)
+            ops.gemm_tc(A, Bm, M, N, K, c=c, residual=R, c_strides=(M * N, 0) if nbo > 1 else (0, 0),
+                        r_strides=(M * N, 0) if nbo > 1 else (0, 0), **kw)
+            h = ops.Operand.empty(nbo * M, N, "h3", DEV)
+            h.buf.zero_()
+            ops.gemm_tc(A, Bm, M, N, K, h=h, h_split=N, h_strides=(M * h.ld, 0), **kw)
+            torch.cuda.synchronize()
+            return c, h.buf.clone()
+        finally:
+            ops.set_gemm_pair(old)
+
+    c0, h0 = run(False)
+    c1, h1 = run(True)
+    assert torch.isfinite(c0).all()
+    assert torch.equal(c0, c1) and torch.equal(h0.view(torch.uint8), h1.view(torch.uint8))
+    ref = (a.double().view(nbo, M, K) @ w.double().T + bias.double()).view(nbo * M, N)
+    ref = torch.where(ref >= 0, ref, 0.2 * ref) + R.double()
+    assert rel_err(nump(c1), nump(ref)) < 1e-5

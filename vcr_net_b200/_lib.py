@@ -99,6 +99,5 @@ def lib() -> _Lib:
     if _instance is None:
         _instance = _Lib()
         from . import config
-        if config.gemm_pair:
-            _instance.vcr_set_gemm_pair(1)
+        _instance.vcr_set_gemm_pair(config.GEMM_PAIR_CODES[str(config.gemm_pair)])
     return _instance

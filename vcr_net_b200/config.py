@@ -55,6 +55,8 @@ def set_precision(p: str):
     precision = p
 
 
-# 3-term ("h3") GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of SMs; csrc/gemm_tc.cu).  Same results
-# bit for bit; applied to the library when it is loaded (ops.lib()) and switchable with ops.set_gemm_pair().
-gemm_pair = os.environ.get("VCR_GEMM_PAIR", "0") == "1"
+# 3-term ("h3") GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of SMs; csrc/gemm_tc.cu): "auto"
+# (default: pairs except for the residual epilogue at K < 1024, measured with scripts/pair_diag.py), "1" always, "0" never.
+# Same results bit for bit; applied to the library when it is loaded (_lib.lib()) and switchable with ops.set_gemm_pair().
+gemm_pair = os.environ.get("VCR_GEMM_PAIR", "auto")
+GEMM_PAIR_CODES = {"0": 0, "1": 1, "auto": 2}

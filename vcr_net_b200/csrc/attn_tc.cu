@@ -249,6 +249,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float m_used = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int sb = g & 1;
+                // kept keys of this warp's 32 columns as a bit mask: one byte per lane, requested before the wait on S
+                uint32_t km = 0xffffffffu;
+                if (keep != nullptr) {
+                    const int key = j * BKV + hf * 32 + lane;
+                    km = __ballot_sync(0xffffffffu, key < p.Nk && __ldg(keep + key) != 0);
+                }
                 tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
                 tc::tc_fence_after();
                 float s[32];
@@ -279,7 +285,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         float x = s[i] * sc;
                         const int key = key0 + i;
                         if (key >= p.Nk) x = -INFINITY;
-                        else if (keep && !keep[key]) x = -1e9f * kLog2e;
+                        else if (!((km >> i) & 1u)) x = -1e9f * kLog2e;
                         s[i] = x;
                     }
                     sc = 1.f;

@@ -63,7 +63,41 @@ struct Cfg {
 using tc::pack_h2;
 using tc::lo_part;
 
-template <int NTERMS, int FMT, int CTAS>
+// Row-major outputs of one 32 x 32 chunk whose rows all exist and whose accesses are 16-byte aligned.  Every run-time switch
+// of the epilogue is a bit of V (1: fp32 C, 2: operand-format output, 4: residual, 8: LeakyReLU, 16: lo plane), so the
+// 8-row loop is straight-line code: the generic loop spent ~900 issue slots per chunk on predicates and branches, which
+// made the K = 512 GEMMs epilogue-bound (two epilogue warps per scheduler).  Same arithmetic, same order.
+template <int V, int OBF>
+__device__ __forceinline__ void store_rows_full(const float* stg, const float4 b4, const float alpha, const float slope,
+                                                const float4 (&rq)[8], float* c0, const int ldc, __half* h0,
+                                                const int ldh, const long long h_plane, const int rsub, const int c4) {
+    constexpr bool HAS_C = (V & 1) != 0, HAS_H = (V & 2) != 0, HAS_R = (V & 4) != 0, ACT = (V & 8) != 0, PL2 = (V & 16) != 0;
+#pragma unroll
+    for (int itr = 0; itr < 8; ++itr) {
+        const int rl = itr * 4 + rsub;
+        float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((c4 ^ (rl & 7)) << 2));
+        x.x = fmaf(alpha, x.x, b4.x); x.y = fmaf(alpha, x.y, b4.y);
+        x.z = fmaf(alpha, x.z, b4.z); x.w = fmaf(alpha, x.w, b4.w);
+        if (ACT) { x.x = leaky(x.x, slope); x.y = leaky(x.y, slope); x.z = leaky(x.z, slope); x.w = leaky(x.w, slope); }
+        if (HAS_R) { x.x += rq[itr].x; x.y += rq[itr].y; x.z += rq[itr].z; x.w += rq[itr].w; }
+        if (HAS_C) *reinterpret_cast<float4*>(c0 + (size_t)(itr * 4) * ldc) = x;
+        if (HAS_H) {
+            __half* hh = h0 + (size_t)(itr * 4) * ldh;
+            *reinterpret_cast<uint2*>(hh) = make_uint2(pack_h2(x.x, x.y, OBF), pack_h2(x.z, x.w, OBF));
+            if (PL2)
+                *reinterpret_cast<uint2*>(hh + h_plane) =
+                    make_uint2(pack_h2(lo_part(x.x, OBF), lo_part(x.y, OBF), OBF),
+                               pack_h2(lo_part(x.z, OBF), lo_part(x.w, OBF), OBF));
+        }
+    }
+}
+
+// MC = 2 (with CTAS = 2): a cluster is TWO pairs working on the same 256 rows and adjacent 128-column tiles.  The A tile is
+// the same for both pairs, so each of the four CTAs fetches one 64-row quarter of the 256 x 64 A block and MULTICASTS it to
+// its counterpart in the other pair: 32 KB instead of 48 KB of L2 -> SM traffic per CTA and k-block.  The main loop is
+// bound by the L2 slice throughput (~6300 B/clk chip-wide = 42 B/clk/SM; 64 KB per 768 MMA-clocks = 83 B/clk wanted by the
+// single-CTA kernel, 62 by a pair, 42 by this one).  A stage is refilled only after BOTH pairs have consumed it.
+template <int NTERMS, int FMT, int CTAS, int MC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
     using C_ = Cfg<NTERMS, CTAS>;
@@ -79,19 +113,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // a scheduling unit is a 128-row tile (CTAS = 1) or a 256-row tile pair (CTAS = 2: this CTA takes rows rank*128..)
-    const int tiles_m = (p.M + CTAS * BM - 1) / (CTAS * BM), tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (p.M + CTAS * BM - 1) / (CTAS * BM), tiles_n = ((p.N + BN - 1) / BN + MC - 1) / MC;
     const int tiles_per_z = tiles_m * tiles_n;
     const long long total_tiles = (long long)tiles_per_z * p.nb_outer * p.nb_inner;
     const int nkb = (p.K + BK - 1) / BK;
-    const int rank = CTAS == 2 ? (int)tc::cluster_ctarank() : 0;
-    const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
+    const int crank = CTAS == 2 ? (int)tc::cluster_ctarank() : 0;
+    const int rank = crank & 1, pairq = crank >> 1;          // rank within the pair, pair within the cluster
+    const int unit0 = blockIdx.x / (CTAS * MC), unit_step = gridDim.x / (CTAS * MC);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C_::NSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C_::NSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MC); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS * 32 * CTAS); }
         tc::fence_barrier_init();
     }
@@ -111,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int s = 0; uint32_t ph = 0;
             for (long long t = unit0; t < total_tiles; t += unit_step) {
                 const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
-                const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = r % tiles_n;
+                const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = (r % tiles_n) * MC + pairq;
                 const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
                 const int a_row = (int)(zo * p.a_row_o + zi * p.a_row_i) + m_blk * BM;
                 const int b_row = (int)(zo * p.b_row_o + zi * p.b_row_i) + n_blk * BN + rank * (BN / CTAS);
@@ -125,7 +160,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (rank == 0) tc::mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);
 #pragma unroll
                         for (int pl = 0; pl < C_::PLANES; ++pl) {
-                            tc::tma_load_3d_2sm(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
+                            if (MC == 2)     // this CTA's 64-row half of the A tile, to itself and its counterpart in the other pair
+                                tc::tma_load_3d_2sm_mc(st + pl * TILE_BYTES + pairq * (TILE_BYTES / 2), &tmA, &full[s],
+                                                       a_col + kb * BK, a_row + pairq * (BM / 2), pl, (uint16_t)(5u << rank));
+                            else
+                                tc::tma_load_3d_2sm(st + pl * TILE_BYTES, &tmA, &full[s], a_col + kb * BK, a_row, pl);
                             tc::tma_load_3d_2sm(st + C_::PLANES * TILE_BYTES + pl * C_::B_TILE_BYTES, &tmB, &full[s],
                                                 b_col + kb * BK, b_row, pl);
                         }
@@ -182,11 +221,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if (CTAS == 2) tc::umma_commit_2sm(&empty[s]);   // frees the stage in both CTAs
+                    if (CTAS == 2) tc::umma_commit_2sm(&empty[s], MC == 2 ? 15 : 3);   // frees the stage in every CTA that fills it
                     else tc::umma_commit(&empty[s]);               // smem slot free once these MMAs retire
                     if (++s == C_::NSTAGES) { s = 0; ph ^= 1; }
                 }
-                if (CTAS == 2) tc::umma_commit_2sm(&tfull[a]);      // both CTAs' epilogues
+                if (CTAS == 2) tc::umma_commit_2sm(&tfull[a], (uint16_t)(3u << (2 * pairq)));   // both CTAs' epilogues
                 else tc::umma_commit(&tfull[a]);                    // accumulator ready for the epilogue
             }
         }
@@ -213,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int it = 0;
         for (long long t = unit0; t < total_tiles; t += unit_step, ++it) {
             const int z = (int)(t / tiles_per_z), r = (int)(t - (long long)z * tiles_per_z);
-            const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = r % tiles_n;
+            const int m_blk = (r / tiles_n) * CTAS + rank, n_blk = (r % tiles_n) * MC + pairq;
             const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -314,7 +353,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                            pack_h2(lo_part(x[q * 8 + 6], obf), lo_part(x[q * 8 + 7], obf), obf));
                     }
                 }
-                if (rowmajor && fast) {
+                if (rowmajor && fast && row0 + 32 <= M) {
+                    const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int vsel = (Cz ? 1 : 0) | (want_h ? 2 : 0) | (Rz ? 4 : 0) | (act == 1 ? 8 : 0) |
+                                     (want_h && nplanes == 2 ? 16 : 0);
+                    float* c0p = Cz ? Cz + (size_t)(row0 + rsub) * ldc + col : nullptr;
+                    __half* h0p = want_h ? Hz + (size_t)(row0 + rsub) * ldh + col : nullptr;
+                    // warp-uniform switch; direct calls keep rq[] in registers
+#define VCR_ROWS_CASE(v) \
+    case v: store_rows_full<v, FMT == 1 ? 1 : 0>(stg, b4, alpha, slope, rq, c0p, ldc, h0p, ldh, p.h_plane, rsub, c4); break;
+                    switch (vsel) {
+                        VCR_ROWS_CASE(1) VCR_ROWS_CASE(5) VCR_ROWS_CASE(9) VCR_ROWS_CASE(13)
+                        VCR_ROWS_CASE(2) VCR_ROWS_CASE(6) VCR_ROWS_CASE(10) VCR_ROWS_CASE(14)
+                        VCR_ROWS_CASE(3) VCR_ROWS_CASE(7) VCR_ROWS_CASE(11) VCR_ROWS_CASE(15)
+                        VCR_ROWS_CASE(18) VCR_ROWS_CASE(22) VCR_ROWS_CASE(26) VCR_ROWS_CASE(30)
+                        VCR_ROWS_CASE(19) VCR_ROWS_CASE(23) VCR_ROWS_CASE(27) VCR_ROWS_CASE(31)
+                        default: break;
+                    }
+#undef VCR_ROWS_CASE
+                } else if (rowmajor && fast) {
                     const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr) {
@@ -374,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (!waited) { tc::mbar_wait(&tfull[a], aph); tc::tc_fence_after(); }
             tc::tc_fence_before();
-            if (CTAS == 2) tc::mbar_arrive_cluster(&tempty[a], 0);   // the leader's MMA issuer waits for both CTAs
+            if (CTAS == 2) tc::mbar_arrive_cluster(&tempty[a], crank & ~1);   // the pair leader's MMA issuer waits for both CTAs
             else tc::mbar_arrive(&tempty[a]);
         }
     }
@@ -407,44 +464,62 @@ __global__ void to_operand_kernel(const float* __restrict__ x, int ld, long long
     }
 }
 
-// CTA-pair launch (cta_group::2): cluster (2,1,1), one pair per TPC.  Returns VCR_ERR_UNSUPPORTED when the device cannot
-// co-schedule pairs (the caller then uses the single-CTA kernel).
+// CTA-pair launch (cta_group::2): cluster of 2 * MC CTAs (MC = 2: two pairs sharing the multicast A tile).  Returns
+// VCR_ERR_UNSUPPORTED when the device cannot co-schedule such a cluster (the caller then uses a smaller variant).
+template <int MC>
 int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams& p, cudaStream_t stream) {
     using C_ = Cfg<3, 2>;
-    auto kern = gemm_tc_kernel<3, 0, 2>;
-    static int max_pairs = -1;             // idempotent, benign race
-    if (max_pairs < 0) {
+    constexpr int CL = 2 * MC;
+    auto kern = gemm_tc_kernel<3, 0, 2, MC>;
+    static int max_clusters = -1;             // idempotent, benign race
+    if (max_clusters < 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
             return VCR_ERR_LAUNCH;
         cudaLaunchConfig_t q = {};
-        q.gridDim = dim3(2, 1, 1); q.blockDim = dim3(NTHREADS, 1, 1); q.dynamicSmemBytes = C_::SMEM_BYTES;
+        q.gridDim = dim3(CL, 1, 1); q.blockDim = dim3(NTHREADS, 1, 1); q.dynamicSmemBytes = C_::SMEM_BYTES;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         q.attrs = at; q.numAttrs = 1;
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        max_pairs = n;
+        max_clusters = n;
     }
-    if (max_pairs < 1) return VCR_ERR_UNSUPPORTED;
-    const long long units = (long long)vcr_cdiv(p.M, 2 * BM) * vcr_cdiv(p.N, BN) * p.nb_outer * p.nb_inner;
-    const int pairs = (int)(units < max_pairs ? units : max_pairs);
+    if (max_clusters < 1) return VCR_ERR_UNSUPPORTED;
+    const long long units = (long long)vcr_cdiv(p.M, 2 * BM) * vcr_cdiv(vcr_cdiv(p.N, BN), MC) * p.nb_outer * p.nb_inner;
+    const int clusters = (int)(units < max_clusters ? units : max_clusters);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs, 1, 1); cfg.blockDim = dim3(NTHREADS, 1, 1);
+    cfg.gridDim = dim3(CL * clusters, 1, 1); cfg.blockDim = dim3(NTHREADS, 1, 1);
     cfg.dynamicSmemBytes = C_::SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p) != cudaSuccess) { cudaGetLastError(); return VCR_ERR_LAUNCH; }
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
 
+// clusters of 4 the device can co-schedule (0 when unsupported); diagnostic for the quad variant
+int quad_clusters() {
+    using C_ = Cfg<3, 2>;
+    auto kern = gemm_tc_kernel<3, 0, 2, 2>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess) return 0;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(4, 1, 1); q.blockDim = dim3(NTHREADS, 1, 1); q.dynamicSmemBytes = C_::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    q.attrs = at; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    return n;
+}
+
 template <int NTERMS, int FMT>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams& p, cudaStream_t stream) {
     using C_ = Cfg<NTERMS>;
-    auto kern = gemm_tc_kernel<NTERMS, FMT, 1>;
+    auto kern = gemm_tc_kernel<NTERMS, FMT, 1, 1>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
         return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
@@ -459,7 +534,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams
 
 }  // namespace
 
-static int g_vcr_gemm_pair = 0;
+static int g_vcr_gemm_pair = 2;      // 0: never, 1: always, 2: auto (see vcr_set_gemm_pair)
 
 vcr_tmap_encode_fn vcr_get_tmap_encoder() {
     static vcr_tmap_encode_fn fn = nullptr;
@@ -525,12 +600,25 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
     p.h_split = H ? (HT ? h_split : N) : 0;
     p.HT = reinterpret_cast<__half*>(HT); p.ldt = ldt; p.t_plane = t_plane; p.t_so = t_so; p.t_si = t_si;
     p.out_planes = out_planes; p.out_bf16 = mode == 2;
-    if (mode == 0 && g_vcr_gemm_pair) {
+    // auto: pairs everywhere except the residual epilogue at K < 1024, the one shape class where the pair measured slower
+    // (0.94-0.97x; 1.03-1.12x elsewhere, scripts/pair_diag.py on B200)
+    const int pol = g_vcr_gemm_pair;
+    if (mode == 0 && pol == 3) {
+        // two pairs per cluster, A multicast: both CTAs of a pair fetch 64-row boxes of A and of B
+        CUtensorMap tmA2, tmB2;
+        rc = vcr_make_operand_tmap(&tmA2, A, a_cols_total, a_rows_total, lda, a_plane, planes, BM / 2);
+        if (rc != VCR_OK) return rc;
+        rc = vcr_make_operand_tmap(&tmB2, B, b_cols_total, b_rows_total, ldb, b_plane, planes, BN / 2);
+        if (rc != VCR_OK) return rc;
+        rc = launch_tc_pair<2>(tmA2, tmB2, p, stream);
+        if (rc != VCR_ERR_UNSUPPORTED) return rc;
+    }
+    if (mode == 0 && (pol == 1 || pol == 3 || (pol == 2 && (R == nullptr || K >= 1024)))) {
         // CTA pairs (cta_group::2): each CTA of a pair stages half of the B tile (box of 64 rows)
         CUtensorMap tmB2;
         rc = vcr_make_operand_tmap(&tmB2, B, b_cols_total, b_rows_total, ldb, b_plane, planes, BN / 2);
         if (rc != VCR_OK) return rc;
-        rc = launch_tc_pair(tmA, tmB2, p, stream);
+        rc = launch_tc_pair<1>(tmA, tmB2, p, stream);
         if (rc != VCR_ERR_UNSUPPORTED) return rc;
     }
     if (mode == 0) return launch_tc<3, 0>(tmA, tmB, p, stream);
@@ -538,10 +626,14 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
     return launch_tc<1, 1>(tmA, tmB, p, stream);
 }
 
-// Process-wide switch: run the 3-term ("h3") GEMMs on CTA pairs (cta_group::2).  Returns the previous setting.
+// Process-wide policy for the 3-term ("h3") GEMMs on CTA pairs (cta_group::2): 0 never, 1 always, 2 auto (default),
+// 3 clusters of two pairs with the A tile multicast (falls back to pairs when such clusters cannot be scheduled).
+// Returns the previous setting.  Results are bit-identical under every setting.
+VCR_API int vcr_gemm_quad_clusters(void) { return quad_clusters(); }
+
 VCR_API int vcr_set_gemm_pair(int on) {
     const int old = g_vcr_gemm_pair;
-    g_vcr_gemm_pair = on ? 1 : 0;
+    g_vcr_gemm_pair = on < 0 ? 0 : (on > 3 ? 2 : on);
     return old;
 }
 

@@ -236,9 +236,11 @@ def gemm_tc(a: Operand, b: Operand, M, N, K, *, nbo=1, nbi=1,
         outp.planes if outp is not None else 1, _stream(a.buf)), "vcr_gemm_tc")
 
 
-def set_gemm_pair(on: bool) -> bool:
-    """Run the h3 GEMMs on CTA pairs (tcgen05 cta_group::2); returns the previous setting.  Results are bit-identical."""
-    return bool(lib().vcr_set_gemm_pair(int(bool(on))))
+def set_gemm_pair(policy):
+    """CTA-pair (tcgen05 cta_group::2) policy of the h3 GEMMs: False / 0 never, True / 1 always, "auto" / 2 (default).
+    Returns the previous policy code.  Results are bit-identical under every setting."""
+    code = 2 if policy == "auto" else int(policy)
+    return lib().vcr_set_gemm_pair(code)
 
 
 def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, Nk, dk, scale, keep=None, lse=None):
