@@ -19,6 +19,11 @@ timeout 300 python scripts/step_profile.py h3 partial > gpurun_out/step_profile_
 timeout 600 python bench.py --steps 5 --warmup 3 --workload whole --num-points 4096 --batch 32 --no-cpu-baseline --no-other-workloads > gpurun_out/bench_whole_4096_b32.json 2> gpurun_out/bench_whole_4096_b32.err
 cat gpurun_out/bench_whole_4096_b32.json; tail -3 gpurun_out/bench_whole_4096_b32.err
 timeout 300 python scripts/knn_bench.py > gpurun_out/knn_bench.txt 2>&1
+# CTA-pair / quad GEMM variants vs the single-CTA kernel (bit-identity + timing), small-batch latency eager vs CUDA graph,
+# and the default bench with the pair kernel off (A/B record)
+timeout -s KILL 150 python scripts/pair_diag.py > gpurun_out/pair_diag.txt 2>&1
+timeout -s KILL 200 python scripts/graph_latency.py > gpurun_out/graph_latency.txt 2>&1
+VCR_GEMM_PAIR=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-workloads > gpurun_out/bench_default_pair0.json 2> gpurun_out/bench_default_pair0.err
 timeout 600 python scripts/kernel_sweep.py > gpurun_out/kernel_sweep_cfg5.txt 2>&1
 if [ "$1" != "nonc" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_h3.csv \

@@ -46,6 +46,24 @@ def test_no_cpu_fallback():
         V.knn(torch.zeros(1, 3, 64), 20)
     with pytest.raises(RuntimeError):
         V.farthest_point_sample(torch.zeros(1, 3, 64), 4)
+    if not torch.cuda.is_available():
+        from vcr_net_b200.graph import GraphedRegistration
+        with pytest.raises(RuntimeError):
+            GraphedRegistration(net, batch=1, num_points=64)
+
+
+def test_gemm_pair_policy_switch_roundtrip():
+    """The CTA-pair policy is a process-wide setting of the library (no GPU needed to set / read it back)."""
+    from vcr_net_b200 import ops, config
+    assert config.GEMM_PAIR_CODES[str(config.gemm_pair)] in (0, 1, 2)
+    first = ops.set_gemm_pair(False)
+    try:
+        assert ops.set_gemm_pair(True) == 0
+        assert ops.set_gemm_pair("auto") == 1
+        assert ops.set_gemm_pair(3) == 2
+        assert ops.set_gemm_pair(0) == 3
+    finally:
+        ops.set_gemm_pair(first)
 
 
 def test_state_dict_layout_and_t7_roundtrip(tmp_path, ckpt):

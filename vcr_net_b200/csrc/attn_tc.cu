@@ -75,8 +75,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int NTERMS, int FMT>
-__global__ void __launch_bounds__(384, 1)
+// NWQ = softmax warps per TMEM lane quarter (2: a warp owns 32 key columns of its 32 rows, 384 threads; 4: 16 columns,
+// 640 threads).  The softmax is a chain of dependent phases (TMEM load, max, exchange, exp2, split, store) per tile, and
+// with two warps per scheduler the chain's latency, not its ~380 instructions, set the tile period (ncu: tensor pipe
+// 50 % active, stalls on scoreboards and the pair barrier); four warps per scheduler with half the chain each hide it.
+__device__ __forceinline__ int ordered_key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float ordered_val(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+constexpr int kNegInfKey = (int)0x807fffffu;         // ordered_key(-inf)
+
+template <int NTERMS, int FMT, int NWQ>
+__global__ void __launch_bounds__(128 + 128 * NWQ, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using C_ = ACfg<NTERMS>;
@@ -107,13 +115,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
             tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 256);
+            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 128 * NWQ);
         }
-        tc::mbar_init(p_full, 256); tc::mbar_init(p_empty, 1);
-        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 256);
+        tc::mbar_init(p_full, 128 * NWQ); tc::mbar_init(p_empty, 1);
+        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 128 * NWQ);
         tc::fence_barrier_init();
     }
     if (warp == 2) { tc::tmem_alloc(tmem_slot, C_::TMEM_COLS); tc::tmem_relinquish(); }
+    if (NWQ == 4 && warp == 3) {                      // row-maximum slots (3 x 128 ordered-int keys) start at -inf
+        int* mx = reinterpret_cast<int*>(smem + C_::OFF_XCH);
+        for (int i = lane; i < 3 * 128; i += 32) mx[i] = kNegInfKey;
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -229,18 +241,25 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
     } else if (warp >= 4) {
         // ============================== softmax + output ==============================
-        // 8 warps: warp w owns query rows (TMEM lanes) 32*(w%4)..+32 and key columns 32*hf..+32 of the tile
-        // (hf = (w-4)/4).  The two warps of a row quarter exchange their partial row maxima through smem
-        // (pair barrier, 64 threads) so both use the same running maximum; the partial sums l are combined
-        // once per item.  Each warp rescales / writes out its half of the O columns.
+        // 4 * NWQ warps: warp w owns query rows (TMEM lanes) 32*(w%4)..+32 and key columns CW*hf..+CW of the tile
+        // (hf = (w-4)/4, CW = 64 / NWQ).  The warps of a row quarter agree on the running maximum through smem (quarter
+        // barrier): NWQ = 2 exchanges fp32 values in two alternating slots, NWQ = 4 takes an atomic max of order-preserving
+        // integer keys in three rotating slots (the 2 KB exchange area cannot hold 2 x 4 x 128 floats; the slot of tile
+        // g + 2 is reset after the barrier of tile g, when every reader of tile g - 1 has passed).  The partial sums l
+        // are combined once per item in a fixed order.  Each warp rescales / writes out its DK / NWQ columns of O.
+        constexpr int CW = BKV / NWQ;                 // key columns per warp
+        constexpr int OW = DK / NWQ;                  // O columns per warp
+        constexpr int OC = NWQ == 4 ? 16 : 32;        // O write-out chunk (register budget: 96 / thread at 640 threads)
         const int qq = warp & 3, hf = (warp - 4) >> 2;
         const int rloc = qq * 32 + lane;
         const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
         const int obf = p.out_bf16;
         uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
-        float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // [2 slots][2 halves][128 rows]
-        auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory"); };
+        float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // NWQ = 2: [2 slots][2][128]; l exchange: [NWQ][128]
+        int* mxk = reinterpret_cast<int*>(smem + C_::OFF_XCH);          // NWQ = 4: [3 slots][128] ordered keys
+        auto pair_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + qq), "r"(32 * NWQ) : "memory"); };
         uint32_t g = 0, w = 0;
+        int g3 = 0;                                                       // g % 3
         for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
             const int qt = (int)(it % nqt);
             const int bh = (int)(it / nqt);
@@ -249,39 +268,41 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float m_used = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int sb = g & 1;
-                // kept keys of this warp's 32 columns as a bit mask: one byte per lane, requested before the wait on S
+                // kept keys of this warp's columns as a bit mask: one byte per lane, requested before the wait on S
                 uint32_t km = 0xffffffffu;
                 if (keep != nullptr) {
-                    const int key = j * BKV + hf * 32 + lane;
+                    const int key = j * BKV + hf * CW + (lane & (CW - 1));
                     km = __ballot_sync(0xffffffffu, key < p.Nk && __ldg(keep + key) != 0);
                 }
                 tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
                 tc::tc_fence_after();
-                float s[32];
+                float s[CW];
                 {
-                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr + hf * 32;
-                    uint32_t r0[32];
-                    tc::tmem_ld_32x32(sa, r0);
+                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr + hf * CW;
+                    uint32_t r0[CW];
+                    if (CW == 32) tc::tmem_ld_32x32(sa, reinterpret_cast<uint32_t(&)[32]>(r0));
+                    else tc::tmem_ld_32x16(sa, reinterpret_cast<uint32_t(&)[16]>(r0));
                     if (NTERMS == 3) {
-                        uint32_t r1[32];
-                        tc::tmem_ld_32x32(sa + BKV, r1);
+                        uint32_t r1[CW];
+                        if (CW == 32) tc::tmem_ld_32x32(sa + BKV, reinterpret_cast<uint32_t(&)[32]>(r1));
+                        else tc::tmem_ld_32x16(sa + BKV, reinterpret_cast<uint32_t(&)[16]>(r1));
                         tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) s[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
+                        for (int i = 0; i < CW; ++i) s[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
                     } else {
                         tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
+                        for (int i = 0; i < CW; ++i) s[i] = __uint_as_float(r0[i]);
                     }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2
                 // ---- (mask,) partial row maximum ----
-                const int key0 = j * BKV + hf * 32;
+                const int key0 = j * BKV + hf * CW;
                 float sc = p.scale_log2;                          // exp2(s*sc - m) below
                 if (keep != nullptr || j * BKV + BKV > p.Nk) {    // warp-uniform: ragged or masked tile
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < CW; ++i) {
                         float x = s[i] * sc;
                         const int key = key0 + i;
                         if (key >= p.Nk) x = -INFINITY;
@@ -292,12 +313,21 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 float mt = s[0];
 #pragma unroll
-                for (int i = 1; i < 32; ++i) mt = fmaxf(mt, s[i]);
+                for (int i = 1; i < CW; ++i) mt = fmaxf(mt, s[i]);
                 mt *= sc;                                         // sc > 0
-                float* slot = xch + (g & 1) * 256;
-                slot[hf * 128 + rloc] = mt;
-                pair_bar();
-                mt = fmaxf(mt, slot[(hf ^ 1) * 128 + rloc]);
+                if (NWQ == 2) {
+                    float* slot = xch + (g & 1) * 256;
+                    slot[hf * 128 + rloc] = mt;
+                    pair_bar();
+                    mt = fmaxf(mt, slot[(hf ^ 1) * 128 + rloc]);
+                } else {
+                    atomicMax(mxk + g3 * 128 + rloc, ordered_key(mt));
+                    pair_bar();
+                    mt = ordered_val(mxk[g3 * 128 + rloc]);
+                    const int g3n = g3 == 0 ? 2 : g3 - 1;         // (g + 2) % 3: last read at tile g - 1
+                    if (hf == 0) mxk[g3n * 128 + rloc] = kNegInfKey;
+                    g3 = g3 == 2 ? 0 : g3 + 1;
+                }
                 float factor = 1.f;
                 bool need = false;
                 if (j == 0) {
@@ -310,7 +340,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const float neg_m = -m_used;
                 float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < CW; i += 2) {
                     s[i] = ex2_approx(fmaf(s[i], sc, neg_m));         rs0 += s[i];
                     s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m)); rs1 += s[i + 1];
                 }
@@ -320,8 +350,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 if (__any_sync(0xffffffffu, need)) {
                     tc::tc_fence_after();
 #pragma unroll 1
-                    for (int c = 0; c < PL * 64; c += 32) {       // this warp's half of D0 (and of D1)
-                        const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + (c >= 64 ? DK - 64 : 0) + hf * 64 + c;
+                    for (int c = 0; c < PL * OW; c += 32) {       // this warp's OW columns of D0 (and of D1)
+                        const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + (c >= OW ? DK - OW : 0) + hf * OW + c;
                         uint32_t r[32];
                         tc::tmem_ld_32x32(oa, r);
                         tc::tmem_ld_wait();
@@ -332,10 +362,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     tmem_st_wait();
                     tc::tc_fence_before();
                 }
-                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: 4 x 16-byte chunks per plane ----
+                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: CW / 8 16-byte chunks per plane ----
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int pos = ((hf * 4 + c) ^ (rloc & 7)) * 16;
+                for (int c = 0; c < CW / 8; ++c) {
+                    const int pos = ((hf * (CW / 8) + c) ^ (rloc & 7)) * 16;
                     uint32_t wv[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) wv[q] = tc::pack_h2(s[c * 8 + 2 * q], s[c * 8 + 2 * q + 1], obf);
@@ -350,38 +380,49 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tc::fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
                 tc::mbar_arrive(p_full);
             }
-            // ---- item done: combine the two partial sums, O / l -> operand-format output (this warp's 64 columns) ----
+            // ---- item done: combine the partial sums (fixed order), O / l -> operand-format output (this warp's OW columns) ----
             pair_bar();
             xch[hf * 128 + rloc] = l;
             pair_bar();
-            l += xch[(hf ^ 1) * 128 + rloc];
+            if (NWQ == 2) {
+                l += xch[(hf ^ 1) * 128 + rloc];
+            } else {
+                l = (xch[rloc] + xch[128 + rloc]) + (xch[256 + rloc] + xch[384 + rloc]);
+            }
             pair_bar();
+            if (NWQ == 4) {                                       // the l exchange overwrote the maximum slots
+                if (hf == 0) { mxk[rloc] = kNegInfKey; mxk[128 + rloc] = kNegInfKey; mxk[256 + rloc] = kNegInfKey; }
+                pair_bar();
+                g3 = 0;
+            }
             tc::mbar_wait(o_full, w & 1);
             tc::tc_fence_after();
             const int q = qt * BQ + rloc;
             const bool q_ok = q < p.Nq;
             const float inv_l = 1.f / l;
-            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + hf * 64;
-            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK + hf * 64;
+            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + hf * OW;
+            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK + hf * OW;
 #pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t r0[32];
-                float v[32];
-                tc::tmem_ld_32x32(oa + c, r0);
+            for (int c = 0; c < OW; c += OC) {
+                uint32_t r0[OC];
+                float v[OC];
+                if (OC == 32) tc::tmem_ld_32x32(oa + c, reinterpret_cast<uint32_t(&)[32]>(r0));
+                else tc::tmem_ld_32x16(oa + c, reinterpret_cast<uint32_t(&)[16]>(r0));
                 if (NTERMS == 3) {
-                    uint32_t r1[32];
-                    tc::tmem_ld_32x32(oa + DK + c, r1);
+                    uint32_t r1[OC];
+                    if (OC == 32) tc::tmem_ld_32x32(oa + DK + c, reinterpret_cast<uint32_t(&)[32]>(r1));
+                    else tc::tmem_ld_32x16(oa + DK + c, reinterpret_cast<uint32_t(&)[16]>(r1));
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
+                    for (int i = 0; i < OC; ++i) v[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
                 } else {
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * inv_l;
+                    for (int i = 0; i < OC; ++i) v[i] = __uint_as_float(r0[i]) * inv_l;
                 }
                 if (q_ok) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
+                    for (int i = 0; i < OC; i += 8) {
                         uint32_t wv[4];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) wv[t] = tc::pack_h2(v[i + 2 * t], v[i + 2 * t + 1], obf);
@@ -405,17 +446,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
 }
 
-template <int NTERMS, int FMT>
+template <int NTERMS, int FMT, int NWQ>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
     using C_ = ACfg<NTERMS>;
-    auto kern = flash_attn_tc_kernel<NTERMS, FMT>;
+    auto kern = flash_attn_tc_kernel<NTERMS, FMT, NWQ>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long items = (long long)p.B * p.H * ((p.Nq + BQ - 1) / BQ);
     const int grid = (int)(items < sms ? items : sms);
-    kern<<<grid, 384, C_::SMEM, st>>>(tq, tk, tv, p);
+    kern<<<grid, 128 + 128 * NWQ, C_::SMEM, st>>>(tq, tk, tv, p);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
