@@ -30,5 +30,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_launch.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_h3.csv > gpurun_out/launches_h3_summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|flash_attn|knn_select|edgeconv_dg_tc|attn_colsum|softcorr_tc' -s 60 -c 28 \
-    -f -o gpurun_out/prof_h3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_full.log 2>&1
+    -f -o /tmp/prof_h3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_full.log 2>&1
+# the .ncu-rep (60 MB) would push gpurun_out/ past the 64 MiB that travel back: export what the summaries need here
+ncu -i /tmp/prof_h3.ncu-rep --page raw --csv > gpurun_out/prof_h3_raw.csv 2>> gpurun_out/ncu_full.log
+python scripts/summarize_ncu_full.py gpurun_out/prof_h3_raw.csv > gpurun_out/ncu_full_summary.txt
+python scripts/ncu_traffic.py gpurun_out/prof_h3_raw.csv > gpurun_out/ncu_traffic.json
 fi

@@ -597,8 +597,16 @@ def _attn_operands(q, k, v, mode):
     return ops.to_operand(tok(q), mode), ops.to_operand(tok(k), mode), ops.to_operand(vt, mode)
 
 
+@pytest.fixture(params=[2, 4])
+def flash_warps(request):
+    """Both softmax-warp layouts of the flash attention kernel (8 / 16 softmax warps per CTA)."""
+    old = ops.set_flash_warps(request.param)
+    yield request.param
+    ops.set_flash_warps(old)
+
+
 @pytest.mark.parametrize("mode,tol", [("h3", 2e-5), ("fp16", 3e-3), ("bf16", 3e-2)])
-def test_flash_attention_vs_golden(mode, tol):
+def test_flash_attention_vs_golden(mode, tol, flash_warps):
     g = load_golden("attention")
     q, k, v = g["q"], g["k"], g["v"]
     B, h, Nq, dk = q.shape
@@ -615,7 +623,7 @@ def test_flash_attention_vs_golden(mode, tol):
 
 
 @pytest.mark.parametrize("Nq,Nk,spread", [(1024, 1024, 1.0), (768, 768, 1.0), (300, 1000, 1.0), (256, 2048, 12.0)])
-def test_flash_attention_shapes_and_rescale(Nq, Nk, spread):
+def test_flash_attention_shapes_and_rescale(Nq, Nk, spread, flash_warps):
     """Ragged tiles, many persistent work items per CTA and (spread = 12) logits whose running maximum
     keeps growing, which exercises the lazy O-rescale path; oracle = numpy attention."""
     rs = np.random.RandomState(Nq + Nk)

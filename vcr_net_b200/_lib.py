@@ -100,4 +100,5 @@ def lib() -> _Lib:
         _instance = _Lib()
         from . import config
         _instance.vcr_set_gemm_pair(config.GEMM_PAIR_CODES[str(config.gemm_pair)])
+        _instance.vcr_set_flash_warps(int(config.flash_warps))
     return _instance

@@ -60,3 +60,8 @@ def set_precision(p: str):
 # Same results bit for bit; applied to the library when it is loaded (_lib.lib()) and switchable with ops.set_gemm_pair().
 gemm_pair = os.environ.get("VCR_GEMM_PAIR", "auto")
 GEMM_PAIR_CODES = {"0": 0, "1": 1, "auto": 2}
+
+
+# flash attention: softmax warps per TMEM lane quarter (2: 8 softmax warps / 384 threads per CTA, 4: 16 / 640); applied to
+# the library when it is loaded, switchable with ops.set_flash_warps()
+flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "2"))

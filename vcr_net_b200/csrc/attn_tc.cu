@@ -463,6 +463,16 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 }  // namespace
 
+static int g_vcr_flash_warps = 2;
+
+// Softmax warps per TMEM lane quarter of the flash attention kernel: 2 (8 softmax warps, 384 threads) or 4 (16 warps,
+// 640 threads).  Process-wide; returns the previous setting.  Results agree to fp32 rounding of the row sums.
+VCR_API int vcr_set_flash_warps(int nwq) {
+    const int old = g_vcr_flash_warps;
+    g_vcr_flash_warps = nwq == 4 ? 4 : 2;
+    return old;
+}
+
 // Q: operand buffer [planes][B*Nq][ldq], head hh in columns [hh*128, hh*128+128) of the given base;
 // K: [planes][B*Nk][ldk] likewise; VT: [planes][B*H*128][ldv] with row (b*H + hh)*128 + d and Nk key columns;
 // O: [planes][B*Nq][ldo] operand-format output (same head layout as Q).  d_k must be 128.
@@ -487,7 +497,12 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
     p.scale_log2 = scale * kLog2e; p.keep = keep;
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
-    if (mode == 0) return launch_attn<3, 0>(tq, tk, tv, p, stream);
-    if (mode == 1) return launch_attn<1, 0>(tq, tk, tv, p, stream);
-    return launch_attn<1, 1>(tq, tk, tv, p, stream);
+    if (g_vcr_flash_warps == 4) {
+        if (mode == 0) return launch_attn<3, 0, 4>(tq, tk, tv, p, stream);
+        if (mode == 1) return launch_attn<1, 0, 4>(tq, tk, tv, p, stream);
+        return launch_attn<1, 1, 4>(tq, tk, tv, p, stream);
+    }
+    if (mode == 0) return launch_attn<3, 0, 2>(tq, tk, tv, p, stream);
+    if (mode == 1) return launch_attn<1, 0, 2>(tq, tk, tv, p, stream);
+    return launch_attn<1, 1, 2>(tq, tk, tv, p, stream);
 }

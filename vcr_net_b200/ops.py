@@ -243,6 +243,11 @@ def set_gemm_pair(policy):
     return lib().vcr_set_gemm_pair(code)
 
 
+def set_flash_warps(nwq: int) -> int:
+    """Softmax warps per TMEM lane quarter of the flash attention kernel (2 or 4); returns the previous setting."""
+    return lib().vcr_set_flash_warps(int(nwq))
+
+
 def flash_attn_tc(q: Operand, k: Operand, vt: Operand, out: Operand, B, H, Nq, Nk, dk, scale, keep=None, lse=None):
     """softmax(Q K^T * scale) V per (batch, head) on tensor cores, nothing of size Nq x Nk touches HBM."""
     L = lib()
