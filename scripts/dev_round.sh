@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout -s KILL 120 python scripts/flash_diag.py > gpurun_out/dev_flash_diag.txt 2>&1; echo "rc=$?" >> gpurun_out/dev_flash_diag.txt
-cat gpurun_out/dev_flash_diag.txt
+timeout -s KILL 200 python -m pytest tests -m gpu -x -q -k "cabi or graphed or cta_pair" > gpurun_out/dev_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/dev_pytest.log; tail -15 gpurun_out/dev_pytest.log
