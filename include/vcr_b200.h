@@ -45,6 +45,10 @@ size_t vcr_knn_workspace_bytes(int B, int N);
 int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
                  int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* D == 3 route of vcr_knn_topk: 1 (default) = distances evaluated on the fly from x|y|z|xx rows in shared memory
+ * (4 CTAs per SM), 0 = the generic distance-tile kernel.  Bit-identical indices; returns the previous setting. */
+int vcr_set_knn3_direct(int on);
+
 /* Tensor-core variant of the same function for feature-space kNN (16 <= D <= 128, k <= 30, token-major only):
  * tcgen05 distance tiles from the operand-format copy of x ([2 planes][B*N][ld] fp16 hi / lo*2^11, vcr_to_operand)
  * prefilter ranks 0..k+8, the survivors are re-ranked with the canonical fp32 chain and certified per query

@@ -146,6 +146,26 @@ def test_knn_tc_matches_simt_inside_lpdnet(net_whole):
         config.knn_tc = old_k
 
 
+@pytest.mark.parametrize("B,N,tm,grid", [(2, 21, False, False), (3, 33, True, False), (2, 777, False, True), (2, 1024, True, True),
+                                         (1, 1500, False, True)])
+def test_knn_3d_direct_and_tile_kernels_agree(B, N, tm, grid):
+    """D == 3 has two routes (on-the-fly distances, default; the generic distance-tile kernel): both equal the canonical
+    oracle bit for bit, on tie-heavy grids too."""
+    rs = np.random.RandomState(N)
+    x = rs.rand(B, 3, N).astype(np.float32) - 0.5
+    if grid:
+        x = np.round(x * 32) / 32
+    xt = cu(x.transpose(0, 2, 1) if tm else x)
+    want = canon.knn(x, 20)
+    for direct in (True, False):
+        old = ops.set_knn3_direct(direct)
+        try:
+            got = nump(ops.knn_topk(xt, 20, token_major=tm))
+        finally:
+            ops.set_knn3_direct(old)
+        assert np.array_equal(got, want), direct
+
+
 def test_knn_duplicates_ties():
     rs = np.random.RandomState(5)
     base = synth.grid_cloud(rs, (1, 3, 64), 3, -0.5, 0.5)      # coarse grid: many exact ties / duplicates

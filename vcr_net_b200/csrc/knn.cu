@@ -376,6 +376,141 @@ int launch_knn(const float* x, const float* xx, int B, int D, int N, int k, int3
 }
 
 // =====================================================================================================
+// 3-d kNN (the xyz graphs of LPDNet's SN1 / DGCNN): distances on the fly.  With D = 3 a distance is three FMAs, so the
+// generic kernel's 32 x 512 distance tile in shared memory (64 KB, two CTAs per SM) only buys smem traffic and low
+// occupancy for a selection whose shuffle networks are latency-bound.  Here a CTA keeps one 512-candidate chunk of the
+// cloud as x | y | z | xx rows (8 KB) plus the survivor buffers (32 KB); every lane evaluates its 16 candidates of a query
+// straight from those rows -- twice in the first chunk (lane maxima for the threshold, then the filter), once afterwards --
+// with the canonical chain  acc = fma(qz, cz, fma(qy, cy, fma(qx, cx, 0)));  pd = (-xx_j - (-2 acc)) - xx_i,  and the
+// same threshold / ballot-compaction / shuffle-bitonic selection as knn_select_kernel.  4 CTAs per SM.
+// =====================================================================================================
+template <int W, class F>
+__device__ __forceinline__ bool filter_merge_fn(F&& get, const float (&tau)[W], Key (&run)[W], uint2* buf, int j0, int lane) {
+    constexpr int RP = TC / 32;
+    const uint32_t lt = (1u << lane) - 1u;
+    int cnt[W], off[W];
+    int base = 0;
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        off[w] = base;
+        int n = base;
+#pragma unroll
+        for (int r = 0; r < RP; ++r) {
+            const float v = get(w, r);
+            const bool p = v >= tau[w];
+            const uint32_t bal = __ballot_sync(0xffffffffu, p);
+            const int pos = n + __popc(bal & lt);
+            if (p && pos < TC) buf[pos] = make_uint2(~(uint32_t)(j0 + r * 32 + lane), okey(v));
+            n += __popc(bal);
+        }
+        cnt[w] = n - base;
+        base = n;
+    }
+    __syncwarp();
+    if (base > TC) return false;
+    int rounds = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) rounds = max(rounds, (cnt[w] + 31) >> 5);
+    for (int r = 0; r < rounds; ++r) {
+        Key e[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int p = r * 32 + lane;
+            const uint2 t = p < cnt[w] ? buf[off[w] + p] : make_uint2(0u, 0u);
+            e[w].lo = t.x; e[w].hi = t.y;
+        }
+        sort32_desc<W>(e, lane);
+        merge32_desc<W>(run, e, lane);
+    }
+    return true;
+}
+
+constexpr int QW3 = 2;                   // queries per warp (register budget: 64 / thread at 4 CTAs per SM)
+constexpr int TQ3 = QW3 * (NT / 32);     // queries per CTA
+template <bool TOKEN_MAJOR>
+__global__ void __launch_bounds__(NT, 4)
+knn3_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int k,
+            int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+    __shared__ float cs[4][TC];                       // x | y | z | xx of the chunk's candidates
+    __shared__ uint2 surv[NT / 32][TC];               // per-warp survivor buffers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, q0 = blockIdx.x * TQ3;
+    const float* xb = x + (size_t)b * 3 * N;
+    const float* xxb = xx + (size_t)b * N;
+
+    float qx[QW3], qy[QW3], qz[QW3], xxq[QW3];
+#pragma unroll
+    for (int w = 0; w < QW3; ++w) {
+        const int q = min(q0 + warp * QW3 + w, N - 1);  // queries past N are computed and not written
+        qx[w] = TOKEN_MAJOR ? xb[(size_t)q * 3 + 0] : xb[q];
+        qy[w] = TOKEN_MAJOR ? xb[(size_t)q * 3 + 1] : xb[(size_t)N + q];
+        qz[w] = TOKEN_MAJOR ? xb[(size_t)q * 3 + 2] : xb[2 * (size_t)N + q];
+        xxq[w] = xxb[q];
+    }
+    Key run[QW3];
+#pragma unroll
+    for (int w = 0; w < QW3; ++w) run[w].hi = run[w].lo = 0u;
+    uint2* buf = surv[warp];
+
+    for (int j0 = 0; j0 < N; j0 += TC) {
+        __syncthreads();                               // the previous chunk's rows are no longer read
+        for (int c = tid; c < TC; c += NT) {
+            const int g = j0 + c;
+            const bool ok = g < N;
+            cs[0][c] = ok ? (TOKEN_MAJOR ? xb[(size_t)g * 3 + 0] : xb[g]) : 0.f;
+            cs[1][c] = ok ? (TOKEN_MAJOR ? xb[(size_t)g * 3 + 1] : xb[(size_t)N + g]) : 0.f;
+            cs[2][c] = ok ? (TOKEN_MAJOR ? xb[(size_t)g * 3 + 2] : xb[2 * (size_t)N + g]) : 0.f;
+            cs[3][c] = ok ? xxb[g] : 0.f;
+        }
+        __syncthreads();
+        auto pd = [&](int w, int r) -> float {
+            const int c = r * 32 + lane;
+            const float acc = fmaf(qz[w], cs[2][c], fmaf(qy[w], cs[1][c], fmaf(qx[w], cs[0][c], 0.f)));
+            const float v = __fsub_rn(__fsub_rn(-cs[3][c], -2.f * acc), xxq[w]);
+            return j0 + c < N ? v : -INFINITY;
+        };
+        float tau[QW3];
+        if (j0 == 0) {
+            float m[QW3];
+#pragma unroll
+            for (int w = 0; w < QW3; ++w) {
+                float mm = pd(w, 0);
+#pragma unroll
+                for (int r = 1; r < RPL; ++r) mm = fmaxf(mm, pd(w, r));
+                m[w] = mm;
+            }
+            sort32_desc_f<QW3>(m, lane);
+#pragma unroll
+            for (int w = 0; w < QW3; ++w) tau[w] = __shfl_sync(0xffffffffu, m[w], k);
+        } else {
+#pragma unroll
+            for (int w = 0; w < QW3; ++w) tau[w] = okey_inv(__shfl_sync(0xffffffffu, run[w].hi, k));
+        }
+        if (!filter_merge_fn<QW3>(pd, tau, run, buf, j0, lane)) {
+            // heavy ties: one query at a time, any survivor count fits the buffer
+#pragma unroll
+            for (int w = 0; w < QW3; ++w) {
+                float t1[1] = {tau[w]};
+                Key r1[1] = {run[w]};
+                filter_merge_fn<1>([&](int, int r) { return pd(w, r); }, t1, r1, buf, j0, lane);
+                run[w] = r1[0];
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < QW3; ++w) {
+        const int q = q0 + warp * QW3 + w;
+        if (q < N && lane >= 1 && lane <= k) {
+            const int j = (int)(~run[w].lo);
+            const size_t o = ((size_t)b * N + q) * k + lane - 1;
+            if (idx32) idx32[o] = j;
+            if (idx64) idx64[o] = (int64_t)j;
+        }
+    }
+}
+
+// =====================================================================================================
 // Tensor-core variant for feature-space kNN (16 <= D <= 128, token-major): the exact kernel's geometry (a CTA owns 32
 // queries, 512-candidate chunks, the same warp-per-query selection) with the FP32 FMA phase replaced by tcgen05
 // distance tiles used as a PREFILTER, then an exact canonical re-rank with a per-query certificate.
@@ -641,6 +776,15 @@ VCR_API size_t vcr_knn_workspace_bytes(int B, int N) { return (size_t)B * N * si
 // x: [B,D,N] (token_major=0, the reference layout) or [B,N,D] (token_major=1); idx: [B,N,k].
 // Either idx32 or idx64 (or both) may be given.  Requires 1 <= k <= 31, N >= k+1; any D >= 1 (D <= 4 is staged
 // 4 dims at a time, wider features 16 dims at a time).
+static int g_vcr_knn3_direct = 1;
+
+// D == 3: distances on the fly (knn3_kernel, default) or the generic tile kernel.  Same indices; returns the previous setting.
+VCR_API int vcr_set_knn3_direct(int on) {
+    const int old = g_vcr_knn3_direct;
+    g_vcr_knn3_direct = on ? 1 : 0;
+    return old;
+}
+
 VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
                          int64_t* idx64, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     VCR_REQUIRE(x && (idx32 || idx64) && B > 0 && N > 0 && k >= 1);
@@ -652,6 +796,13 @@ VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_m
     else knn_sqnorm_kernel<false><<<g, 256, 0, stream>>>(x, D, N, xx);
     VCR_CHECK_LAUNCH();
     if (k > 31) return VCR_ERR_UNSUPPORTED;
+    if (D == 3 && g_vcr_knn3_direct) {
+        dim3 grid(vcr_cdiv(N, TQ3), B);
+        if (token_major) knn3_kernel<true><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);
+        else knn3_kernel<false><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);
+        VCR_CHECK_LAUNCH();
+        return VCR_OK;
+    }
     if (D <= 4)
         return token_major ? launch_knn<4, true>(x, xx, B, D, N, k, idx32, idx64, stream)
                            : launch_knn<4, false>(x, xx, B, D, N, k, idx32, idx64, stream);

@@ -66,6 +66,11 @@ def knn_topk(x: torch.Tensor, k: int, token_major: bool = False, want64: bool = 
     return (idx32, idx64) if want64 else idx32
 
 
+def set_knn3_direct(on: bool) -> bool:
+    """D == 3 route of knn_topk: on-the-fly distances (default) or the generic distance-tile kernel; same indices."""
+    return bool(lib().vcr_set_knn3_direct(int(bool(on))))
+
+
 def knn_topk_tc(x: torch.Tensor, xop, k: int, want64: bool = False, want_flagged: bool = False):
     """Feature-space kNN with the tcgen05 prefilter (csrc/knn.cu): x fp32 token-major [B,N,D], xop its "h3" Operand
     (None: converted here).  Same (bit-identical) result as knn_topk(x, k, token_major=True).
