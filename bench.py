@@ -120,7 +120,7 @@ def run_reference_arm(a, cfg, rank, world):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -445,9 +445,20 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         v, dt = cpu_pairs_per_sec(cfg, a.num_points, a.cpu_sample_pairs)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{a.cpu_sample_pairs} pairs of the same workload, one pass ({dt:.1f} s) of {CPU_ARM}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    """Print the result line on the real stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -460,6 +471,12 @@ def main():
         os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                   f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                   str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:])
+    # stdout carries exactly ONE line (the JSON result): everything else a library prints there (e.g. NCCL's version banner
+    # at communicator creation) is sent to stderr by pointing fd 1 at fd 2 until the result is emitted
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     cfg = workload_cfg(a)
     if a.cpu_sample_pairs <= 0:
         a.cpu_sample_pairs = 12 if cfg["partial"] else 24
