@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout -s KILL 120 python scripts/knn3_diag.py > gpurun_out/dev_knn3_diag.txt 2>&1; echo "rc=$?" >> gpurun_out/dev_knn3_diag.txt
-cat gpurun_out/dev_knn3_diag.txt
-timeout -s KILL 200 python -m pytest tests -m gpu -x -q -k "knn" > gpurun_out/dev_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/dev_pytest.log; tail -8 gpurun_out/dev_pytest.log
+timeout -s KILL 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
+timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout -s KILL 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-workloads 2>/dev/null | cut -c1-400
