@@ -161,12 +161,8 @@ VCR_API int vcr_crop_nearest(const double* pc64, int P, int N, int keep, float* 
     VCR_REQUIRE(pc64 && out && P > 0 && N > 0 && keep > 0 && keep <= N);
     if ((size_t)N * sizeof(double) > 200 * 1024) return VCR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)N * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(crop_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return VCR_ERR_LAUNCH;
-        configured = true;
-    }
+    // set on every launch: the attribute is per device, and one process may drive several (nn.DataParallel)
+    if (cudaFuncSetAttribute(crop_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return VCR_ERR_LAUNCH;
     crop_nearest_kernel<<<P, 256, smem, stream>>>(pc64, N, keep, out);
     VCR_CHECK_LAUNCH();
     return VCR_OK;

@@ -471,8 +471,14 @@ int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmP
     using C_ = Cfg<3, 2>;
     constexpr int CL = 2 * MC;
     auto kern = gemm_tc_kernel<3, 0, 2, MC>;
-    static int max_clusters = -1;             // idempotent, benign race
-    if (max_clusters < 0) {
+    // per device (nn.DataParallel drives several devices from one process): the function attribute and the number of
+    // co-schedulable clusters; idempotent, benign race
+    static int max_clusters_dev[64];
+    static bool known[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & 63;
+    if (!known[slot]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
             return VCR_ERR_LAUNCH;
         cudaLaunchConfig_t q = {};
@@ -483,8 +489,10 @@ int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmP
         q.attrs = at; q.numAttrs = 1;
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        max_clusters = n;
+        max_clusters_dev[slot] = n;
+        known[slot] = true;
     }
+    const int max_clusters = max_clusters_dev[slot];
     if (max_clusters < 1) return VCR_ERR_UNSUPPORTED;
     const long long units = (long long)vcr_cdiv(p.M, 2 * BM) * vcr_cdiv(vcr_cdiv(p.N, BN), MC) * p.nb_outer * p.nb_inner;
     const int clusters = (int)(units < max_clusters ? units : max_clusters);

@@ -212,6 +212,32 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool va
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+
+// one DCH-dim slab of the chunk's TC candidates (rows j0..) and the CTA's TQ queries (rows q0..) of a token-major cloud
+// into Cb [TC][DCP] / Qb [TQ][DCP], as one cp.async group (16-byte pieces; rows / dims past N / D are zero-filled)
+template <int DCH, int DCP>
+__device__ __forceinline__ void issue_slab(const float* __restrict__ xb, int D, int N, int j0, int q0, int d0,
+                                           float* Cb, float* Qb, int tid) {
+    constexpr int PPR = DCH / 4;       // 16-byte pieces per row
+    constexpr int RPP = 256 / PPR;     // rows covered per pass (NT threads)
+    const int part = tid % PPR, r0 = tid / PPR;
+    const bool dok = d0 + 4 * part < D;
+    const float* src = xb + (size_t)(j0 + r0) * D + d0 + 4 * part;
+    float* dst = Cb + r0 * DCP + 4 * part;
+#pragma unroll
+    for (int n = 0; n < 512 / RPP; ++n) {
+        const bool ok = dok && j0 + r0 + n * RPP < N;
+        cp_async16(dst + n * RPP * DCP, ok ? src + (size_t)n * RPP * D : xb, ok);
+    }
+    if (r0 < 32) {
+        const bool ok = dok && q0 + r0 < N;
+        cp_async16(Qb + r0 * DCP + 4 * part, ok ? xb + (size_t)(q0 + r0) * D + d0 + 4 * part : xb, ok);
+    }
+    cp_async_commit();
+}
 
 constexpr int QW = TQ / (NT / 32);   // queries per warp in the selection phase (4)
 constexpr size_t SURV_BYTES = (size_t)(NT / 32) * TC * sizeof(uint2);   // per-warp survivor buffers (alias the operand stage)
@@ -257,23 +283,25 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) acc[qi][ci] = 0.f;
 
-        for (int d0 = 0; d0 < D; d0 += DCH) {
-            __syncthreads();                       // previous compute / selection no longer reads region 0
+        // Operand slabs (DCH dims of the chunk's candidates + the CTA's queries).  The token-major vector path double-buffers
+        // them with cp.async: slab s + 1 streams in while slab s is multiplied; the second buffer aliases the distance tile,
+        // which is only live between the end of this loop and the end of the selection (ncu had 29 % of the warp samples
+        // in the load-and-wait phase of the single-buffered loop).
+        const int nslab = (D + DCH - 1) / DCH;
+        __syncthreads();                           // the previous chunk's selection no longer reads region 0 / dist
+        if (vec) issue_slab<DCH, DCP>(xb, D, N, j0, q0, 0, Cs, Qs, tid);
+        for (int c = tid; c < TC; c += NT) xxc[c] = (j0 + c < N) ? xxb[j0 + c] : 0.f;
+        for (int si = 0; si < nslab; ++si) {
+            const int d0 = si * DCH;
+            const float* Cb = (vec && (si & 1)) ? dist : Cs;
+            const float* Qb = Cb + TC * DCP;
             if (vec) {
-                constexpr int PPR = DCH / 4;       // 16-byte pieces per row
-                constexpr int RPP = NT / PPR;      // rows covered per pass
-                const int part = tid % PPR, r0 = tid / PPR;
-                const bool dok = d0 + 4 * part < D;
-                const float* src = xb + (size_t)(j0 + r0) * D + d0 + 4 * part;
-                float* dst = Cs + r0 * DCP + 4 * part;
-#pragma unroll
-                for (int n = 0; n < TC / RPP; ++n) {
-                    const bool ok = dok && j0 + r0 + n * RPP < N;
-                    cp_async16(dst + n * RPP * DCP, ok ? src + (size_t)n * RPP * D : xb, ok);
-                }
-                if (r0 < TQ) {
-                    const bool ok = dok && q0 + r0 < N;
-                    cp_async16(Qs + r0 * DCP + 4 * part, ok ? xb + (size_t)(q0 + r0) * D + d0 + 4 * part : xb, ok);
+                if (si + 1 < nslab) {
+                    float* Cn = (si & 1) ? Cs : dist;      // last read by slab si - 1, ordered by the trailing barrier
+                    issue_slab<DCH, DCP>(xb, D, N, j0, q0, d0 + DCH, Cn, Cn + TC * DCP, tid);
+                    cp_async_wait_group<1>();
+                } else {
+                    cp_async_wait_group<0>();
                 }
             } else {
                 for (int e = tid; e < (TC + TQ) * DCH; e += NT) {
@@ -288,14 +316,11 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
                     Cs[row * DCP + d] = v;
                 }
             }
-            if (d0 == 0)
-                for (int c = tid; c < TC; c += NT) xxc[c] = (j0 + c < N) ? xxb[j0 + c] : 0.f;
-            if (vec) cp_async_wait_all();
             __syncthreads();
 
-            const float* qrow = Qs + (qg * 8) * DCP;
-            const float* crow = Cs + (cg * 256 + lane) * DCP;
-            if (j0 + cg * 256 >= N) continue;      // this warp's 256 candidates are all past N (e.g. N = 768): warp-uniform
+            const float* qrow = Qb + (qg * 8) * DCP;
+            const float* crow = Cb + (cg * 256 + lane) * DCP;
+            if (j0 + cg * 256 < N) {               // else this warp's 256 candidates are all past N (e.g. N = 768): warp-uniform
 #pragma unroll 1   // (a fully unrolled body makes ptxas rotate the 64 accumulators: +20% MOVs and spills at 128 regs)
             for (int d4 = 0; d4 < DCH / 4; ++d4) {
 #pragma unroll
@@ -319,6 +344,8 @@ knn_select_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
                     }
                 }
             }
+            }
+            __syncthreads();                       // this slab's buffer may be refilled; the last one also orders the dist stores
         }
 
         // distances of this chunk -> dist[q][c]; candidates past N become -inf
@@ -363,12 +390,8 @@ int launch_knn(const float* x, const float* xx, int B, int D, int N, int k, int3
                cudaStream_t st, const int* redo = nullptr) {
     auto kern = knn_select_kernel<DCH, TM>;
     const size_t smem = Smem<DCH>::total;
-    static bool configured = false;     // idempotent attribute, benign race
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return VCR_ERR_LAUNCH;
-        configured = true;
-    }
+    // set on every launch: the attribute is per device, and one process may drive several (nn.DataParallel)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return VCR_ERR_LAUNCH;
     dim3 grid(vcr_cdiv(N, TQ), B);
     kern<<<grid, NT, smem, st>>>(x, xx, D, N, k, i32, i64, redo);
     VCR_CHECK_LAUNCH();

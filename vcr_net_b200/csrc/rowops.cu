@@ -693,12 +693,8 @@ VCR_API int vcr_softmax_colsum(const float* S, int ld, int B, long long rows_per
     if (slabs > 0x7fffffff) return VCR_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < vcr_softmax_colsum_workspace_bytes(B, rows_per_batch, ld, n)) return VCR_ERR_WORKSPACE;
     const size_t smem = ((size_t)rb * ld + rb) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(softmax_colsum_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return VCR_ERR_LAUNCH;
-        configured = true;
-    }
+    // set on every launch: the attribute is per device, and one process may drive several (nn.DataParallel)
+    if (cudaFuncSetAttribute(softmax_colsum_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return VCR_ERR_LAUNCH;
     float* part = reinterpret_cast<float*>(workspace);
     dim3 g((unsigned)slabs, B);
     softmax_colsum_fused_kernel<<<g, 256, smem, stream>>>(S, ld, rows_per_batch, n, rb, part);
