@@ -978,6 +978,34 @@ def test_graphed_registration_is_bit_identical(net_whole, net_partial, partial, 
         reg(src[:B, :, :100], tgt[:B])
 
 
+def test_vcrnet_iter_transparent_graph_cache(net_partial):
+    """config.cuda_graph (VCR_CUDA_GRAPH=1): the reference-facing vcrnetIter serves repeated shapes from a captured graph --
+    first call eager, second captures, later ones replay; fresh result tensors, same bits; an in-place weight update
+    drops the cache."""
+    from vcr_net_b200 import config
+    p = synth.make_pairs(8, 512, partial=True, first_item=33)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    eager = [V.vcrnetIter(net_partial, src[i:i + 2], tgt[i:i + 2], iter=3) for i in (0, 2, 4, 6)]
+    config.cuda_graph = True
+    try:
+        got = [V.vcrnetIter(net_partial, src[i:i + 2], tgt[i:i + 2], iter=3) for i in (0, 2, 4, 6)]
+        cache = net_partial.__dict__["_vcr_graph_cache"]
+        assert len(cache["entries"]) == 1 and next(iter(cache["entries"].values())) != "seen"
+        for e, g in zip(eager, got):
+            for a, b in zip(e, g):
+                assert torch.equal(a, b)
+        assert got[2][2].data_ptr() != got[3][2].data_ptr()            # results are not the graph's static buffers
+        with torch.no_grad():
+            next(net_partial.parameters()).mul_(1.0)                    # bumps the parameter version
+        again = V.vcrnetIter(net_partial, src[:2], tgt[:2], iter=3)
+        assert next(iter(net_partial.__dict__["_vcr_graph_cache"]["entries"].values())) == "seen"
+        for a, b in zip(eager[0], again):
+            assert torch.equal(a, b)
+    finally:
+        config.cuda_graph = False
+        net_partial.__dict__.pop("_vcr_graph_cache", None)
+
+
 @pytest.mark.parametrize("M,N,K,nbo", [(256, 128, 64, 1), (300, 200, 72, 1), (494, 494, 512, 3), (1000, 130, 520, 1),
                                        (64, 64, 64, 5), (2048, 1536, 512, 2)])
 def test_gemm_cta_pair_is_bit_identical(M, N, K, nbo):

@@ -65,3 +65,8 @@ GEMM_PAIR_CODES = {"0": 0, "1": 1, "auto": 2}
 # flash attention: softmax warps per TMEM lane quarter (2: 8 softmax warps / 384 threads per CTA, 4: 16 / 640); applied to
 # the library when it is loaded, switchable with ops.set_flash_warps()
 flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "2"))
+
+
+# vcrnetIter: serve repeated calls of one (network, shapes, iter) from a captured CUDA graph (vcr_net_b200/graph.py;
+# bit-identical outputs, fresh result tensors).  Off by default: the headline numbers go through the eager module API.
+cuda_graph = os.environ.get("VCR_CUDA_GRAPH", "0") == "1"

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-from .model.vcrnet_model import vcrnetIter
+from .model.vcrnet_model import _vcrnet_iter_eager as vcrnetIter
 
 
 class GraphedRegistration:

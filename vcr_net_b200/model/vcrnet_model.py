@@ -13,6 +13,41 @@ from .transformer import Transformer
 
 
 def vcrnetIter(net, src, tgt, iter=1):
+    """model/vcrnet_model.py:21-43 with the reference's signature.  With ``config.cuda_graph`` (env VCR_CUDA_GRAPH=1, off
+    by default) repeated calls with the same network, shapes and ``iter`` are served by a captured CUDA graph
+    (vcr_net_b200/graph.py): the first call of a shape runs eagerly, the second captures, later ones replay; results are
+    fresh tensors and bit-identical to the eager loop; any in-place change of a parameter drops the cache."""
+    from .. import config
+    if (config.cuda_graph and isinstance(net, VCRNet) and not net.training and src.is_cuda
+            and not torch.cuda.is_current_stream_capturing()):
+        return _vcrnet_iter_cached(net, src, tgt, int(iter))
+    return _vcrnet_iter_eager(net, src, tgt, iter)
+
+
+_GRAPH_CACHE_MAX = 4
+
+
+def _vcrnet_iter_cached(net, src, tgt, iter):
+    from .. import config
+    from ..graph import GraphedRegistration
+    stamp = sum(p._version for p in net.parameters())
+    cache = net.__dict__.setdefault("_vcr_graph_cache", {"stamp": stamp, "entries": {}})
+    if cache["stamp"] != stamp:                       # weights were updated in place: captured pointers may be stale
+        cache["stamp"], cache["entries"] = stamp, {}
+    key = (tuple(src.shape), tuple(tgt.shape), iter, str(src.device), config.precision, config.reuse_target_embedding)
+    ent = cache["entries"].get(key)
+    if ent is None:
+        if len(cache["entries"]) >= _GRAPH_CACHE_MAX:
+            cache["entries"].pop(next(k0 for k0 in cache["entries"]))      # oldest shape first
+        cache["entries"][key] = "seen"               # capture on the second call of this shape, not for one-off shapes
+        return _vcrnet_iter_eager(net, src, tgt, iter)
+    if ent == "seen":
+        ent = cache["entries"][key] = GraphedRegistration(net, batch=src.shape[0], num_points=src.shape[2], iter=iter,
+                                                          num_points_tgt=tgt.shape[2])
+    return tuple(o.clone() for o in ent(src, tgt))
+
+
+def _vcrnet_iter_eager(net, src, tgt, iter=1):
     """model/vcrnet_model.py:21-43: refine `iter` times, composing R_f <- R_i R_f, t_f <- R_i t_f + t_i.
 
     The target cloud never changes inside the loop, so its embedding ``emb_nn(tgt)`` is loop-invariant: with
