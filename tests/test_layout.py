@@ -139,3 +139,20 @@ def test_dropin_rebinds_reference_symbols():
     for name in list(sys.modules):                    # leave no reference modules behind for other tests
         if name in ("model", "util") or name.startswith(("model.", "util.")):
             del sys.modules[name]
+
+
+def test_every_entry_point_rejects_null_arguments():
+    """Error behaviour of the boundary: every stream-taking entry point validates its arguments before it touches CUDA
+    and answers an all-null / all-zero call with a negative code (so this runs without a GPU)."""
+    import ctypes
+    from vcr_net_b200._lib import lib
+    L = lib()
+    checked = 0
+    for name, (_, args) in L.protos.items():
+        if not args or args[-1][1] != "stream":
+            continue
+        vals = [None if t is ctypes.c_void_p else t(0) for t, _ in args]
+        rc = getattr(L.cdll, name)(*vals)
+        assert isinstance(rc, int) and rc < 0, (name, rc)
+        checked += 1
+    assert checked >= 50
