@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout -s KILL 200 python -m pytest tests -m gpu -x -q -k "graph or iter or vcrnet" > gpurun_out/dev_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/dev_pytest.log; tail -25 gpurun_out/dev_pytest.log
+timeout -s KILL 200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
