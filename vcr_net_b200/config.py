@@ -20,7 +20,7 @@ reuse_target_embedding = os.environ.get("VCR_REUSE_TGT_EMB", "0") == "1"
 
 
 # feature-space kNN (16 <= D <= 128): tcgen05 prefilter + exact re-rank (csrc/knn.cu, bit-identical indices).
-# Measured on B200 (scripts/knn_bench.py, D = 64, profiles/r01_knn_tc_prefilter_v5.txt): 0.94x of the FP32 SIMT kernel at
+# Measured on B200 (scripts/knn_bench.py, D = 64, profiles/r01_knn_tc_prefilter_v6.txt): 0.94x of the FP32 SIMT kernel at
 # N = 1024 (two 512-candidate chunks per CTA do not amortise the TMA -> MMA -> TMEM latency chain and the re-rank),
 # 1.47x at N = 4096, 1.85x at N = 16384.  "auto" (default) therefore uses it from N >= 2048 in the tensor-core precision
 # modes; "1" always, "0" never.
