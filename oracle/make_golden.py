@@ -175,6 +175,37 @@ def main():
 
     make_lpd_train(ref, lpd_sd)
     make_variants(ref)
+    make_ragged(ref)
+
+
+def make_ragged(ref=None):
+    """Live-reference outputs at the ragged sizes of tests/test_gpu_parity.py::test_vcrnet_ragged_sizes_vs_oracle (odd point
+    counts, one pair; source and target clouds of different sizes) and an odd partial crop with iter=2: pins the oracle where
+    the GPU test leans on it.  Standalone: python -c "from oracle import make_golden as m; m.make_ragged()"."""
+    torch.set_num_threads(1)
+    ref = ref or ref_harness.import_reference()
+    VM = ref.vcrnet_model
+    lpd = dict(np.load(os.path.join(GOLD, "lpd_pretrained_weights.npz")))
+    sd_t = synth.checkpoint_to_torch(synth.make_checkpoint(1234, emb_weights=lpd))
+
+    def build(partial):
+        net = VM.VCRNet(ref_harness.default_args(partial=partial, overlap2=OV2 if partial else 0.75)).eval()
+        net.load_state_dict(sd_t, strict=True)
+        return net
+
+    with torch.no_grad():
+        net_w, net_p = build(False), build(True)
+        p = synth.make_pairs(1, 333, first_item=70)
+        o1 = VM.vcrnetIter(net_w, T(p["src"]), T(p["tgt"]), iter=1)
+        q = synth.make_pairs(2, 300, first_item=80)
+        tgt_short = np.ascontiguousarray(q["tgt"][:, :, :257])
+        o2 = VM.vcrnetIter(net_w, T(q["src"]), T(tgt_short), iter=1)
+        r = synth.make_pairs(1, 331, partial=True, first_item=90)
+        o3 = VM.vcrnetIter(net_p, T(r["src"]), T(r["tgt"]), iter=2)
+    save("vcrnet_ragged",
+         corrK_333=N_(o1[1]), R_333=N_(o1[2]), t_333=N_(o1[3]),
+         corrK_300_257=N_(o2[1]), R_300_257=N_(o2[2]), t_300_257=N_(o2[3]),
+         srcK_p331=N_(o3[0]), corrK_p331=N_(o3[1]), R_p331=N_(o3[2]), t_p331=N_(o3[3]), overlap2=np.array(OV2))
 
 
 def make_lpd_train(ref=None, lpd_sd=None):
@@ -320,6 +351,8 @@ if __name__ == "__main__":
         make_variants()
     elif len(sys.argv) > 1 and sys.argv[1] == "tnet":
         make_tnet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ragged":
+        make_ragged()
     elif len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
         make_lpd_train()
     else:
