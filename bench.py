@@ -385,11 +385,14 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     for name, ms, args in prof:
         d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += ms; d["n"] += 1
-        if name == "vcr_wgrad_f32":                         # streams G [M,N] and X [M,K] (fp32) once, dW is tiny
-            Mw, Nw, Kw = args[4:7]
-            d["bytes"] += 4.0 * Mw * (Nw + Kw) + 4.0 * Nw * Kw
-        elif name == "vcr_layernorm_operand":               # reads fp32 [M,D], writes `planes` 16-bit planes
-            d["bytes"] += (4.0 + 2.0 * args[10]) * args[5] * args[6]
+        try:                                                # reporting only: never let the accounting break a run
+            if name == "vcr_wgrad_f32":                     # streams G [M,N] and X [M,K] (fp32) once, dW is tiny
+                Mw, Nw, Kw = args[4:7]
+                d["bytes"] += 4.0 * Mw * (Nw + Kw) + 4.0 * Nw * Kw
+            elif name == "vcr_layernorm_operand":           # reads fp32 [M,D], writes `planes` 16-bit planes
+                d["bytes"] += (4.0 + 2.0 * args[10]) * args[5] * args[6]
+        except (TypeError, IndexError, ValueError):
+            pass
         if name in ("vcr_gemm_f32", "vcr_gemm_tc"):
             d["flops"] += gemm_flops(args)
         elif name == "vcr_flash_attn_tc":                  # 4 * Nq * Nk * dk per (batch, head): QK^T + PV
