@@ -471,6 +471,8 @@ def emit(line):
     if _STDOUT_FD is not None:
         os.dup2(_STDOUT_FD, 1)
     print(json.dumps(line), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)                                  # anything printed during teardown goes to stderr again
 
 
 def main():
