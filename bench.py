@@ -359,17 +359,19 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
                    "note": "vcr_net_b200.graph.GraphedRegistration: the same vcrnetIter loop captured once and replayed as "
                            "ONE CUDA graph (bit-identical outputs; inputs copied into the graph's static buffers inside "
                            "the timed region); NOT the headline, which goes through the reference-facing module API"}
-    reuse = None
+    nohoist = None
     if cfg["iters"] > 1 and not cfg.get("train") and not a.no_other_workloads:
-        vcfg.reuse_target_embedding = True
+        old_hoist, vcfg.hoist = vcfg.hoist, "none"
         steps3 = max(5, a.steps // 2)
         r3 = measure(a, cfg, rank, world, dev, local_rank, steps3, 3, profile=False)
-        vcfg.reuse_target_embedding = False
+        vcfg.hoist = old_hoist
         m3, e3 = reduce_max(world, dev, r3["ms_total"], r3["ms_e2e"])
-        reuse = {"value": r3["B"] * steps3 * world / (m3 / 1e3), "e2e": r3["B"] * steps3 * world / (e3 / 1e3),
-                 "unit": "pairs/s", "steps": steps3,
-                 "note": "config.reuse_target_embedding=1: emb_nn(tgt) once per call instead of once per iteration; "
-                         "NOT the headline (the default path recomputes it like the reference)"}
+        nohoist = {"value": r3["B"] * steps3 * world / (m3 / 1e3), "e2e": r3["B"] * steps3 * world / (e3 / 1e3),
+                   "unit": "pairs/s", "steps": steps3,
+                   "note": "config.hoist='none': everything that depends on the target cloud alone (emb_nn(tgt), encoder(tgt), "
+                           "the decoder's first self-attention sublayer on tgt) recomputed in every --iter iteration, i.e. "
+                           "exactly the work the reference does per iteration; bit-identical outputs to the default "
+                           "(hoisted) headline"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -449,8 +451,8 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
     }
     if other:
         line["other_workloads"] = other
-    if reuse:
-        line["variant_reuse_target_embedding"] = reuse
+    if nohoist:
+        line["variant_no_hoisting"] = nohoist
     if graphed:
         line["variant_cuda_graph"] = graphed
     if not a.no_cpu_baseline and not cfg.get("train"):

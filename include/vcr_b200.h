@@ -9,8 +9,11 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer (fp32 unless stated), caller-allocated, never retained;
- *   - no hidden allocation, no synchronisation, no global mutable state: calls are thread-safe
- *     and asynchronous on `stream` of the CURRENT device (nn.DataParallel's per-device threads);
+ *   - no hidden allocation and no synchronisation; calls are thread-safe and asynchronous on `stream` of the
+ *     CURRENT device (nn.DataParallel's per-device threads).  The only process-wide state is (a) the launch
+ *     counter, (b) three atomic TUNING knobs that select between bit-identical kernel variants
+ *     (vcr_set_gemm_pair, vcr_set_flash_warps, vcr_set_knn3_direct) and (c) per-device caches of idempotent
+ *     device queries, published with release/acquire atomics -- nothing a result depends on;
  *   - workspace comes from the caller; query its size with the matching *_workspace_bytes();
  *   - return value: 0 = VCR_OK, < 0 = error (the Python wrapper raises RuntimeError):
  *       -1 invalid argument / alignment, -2 unsupported shape, -3 launch failure, -4 workspace;

@@ -346,6 +346,105 @@ def make_tnet(ref=None):
     save("tnet", **out)
 
 
+def _loader_from_pairs(p, batch):
+    """Batches shaped like the reference's DataLoader over ModelNet40.__getitem__ (util/data.py:296-318)."""
+    n = p["src"].shape[0]
+    R_ba = np.transpose(p["R_ab"], (0, 2, 1)).copy()
+    t_ba = -np.einsum("pij,pj->pi", R_ba, p["t_ab"]).astype(np.float32)
+    e_ba = -p["euler_ab"][:, ::-1].copy()
+    out = []
+    for b0 in range(0, n, batch):
+        s = slice(b0, min(n, b0 + batch))
+        out.append((T(p["src"][s]), T(p["tgt"][s]), T(p["R_ab"][s]), T(p["t_ab"][s]), T(R_ba[s]), T(t_ba[s]),
+                    T(p["euler_ab"][s]), T(e_ba[s]), torch.zeros(s.stop - s.start, dtype=torch.int64)))
+    return out
+
+
+def aggregate_metrics(ref, res):
+    """testVCRNet's printed aggregates (model/vcrnet_model.py:776-806) from test_one_epoch's return tuple, through the
+    reference's own npmat2euler."""
+    (loss_pose, cycle, mse_ab, mae_ab, mse_ba, mae_ba, R_ab, t_ab, R_ab_p, t_ab_p, R_ba, t_ba, R_ba_p, t_ba_p,
+     e_ab, e_ba, loss_vcr) = res
+    eul = ref.util.npmat2euler(R_ab_p)
+    r_mse = np.mean((eul - np.degrees(e_ab)) ** 2)
+    t_mse = np.mean((t_ab - t_ab_p) ** 2)
+    eul_ba = ref.util.npmat2euler(R_ba_p, 'xyz')
+    r_mse_ba = np.mean((eul_ba - np.degrees(e_ba)) ** 2)
+    t_mse_ba = np.mean((t_ba - t_ba_p) ** 2)
+    return dict(loss=loss_vcr, loss_pose=loss_pose, cycle_loss=cycle, mse_ab=mse_ab, rmse_ab=np.sqrt(mse_ab), mae_ab=mae_ab,
+                mse_ba=mse_ba, mae_ba=mae_ba,
+                r_mse_ab=r_mse, r_rmse_ab=np.sqrt(r_mse), r_mae_ab=np.mean(np.abs(eul - np.degrees(e_ab))),
+                t_mse_ab=t_mse, t_rmse_ab=np.sqrt(t_mse), t_mae_ab=np.mean(np.abs(t_ab - t_ab_p)),
+                r_mse_ba=r_mse_ba, r_mae_ba=np.mean(np.abs(eul_ba - np.degrees(e_ba))),
+                t_mse_ba=t_mse_ba, t_mae_ba=np.mean(np.abs(t_ba - t_ba_p)))
+
+
+HEADLINE = {   # BASELINE.json configs[0] / configs[1] at their own sizes; 48 items = the staged synthetic test partition
+    "cfg1": dict(partial=False, batch=16, num_points=1024, iters=1, n_pairs=48),
+    "cfg2": dict(partial=True, batch=24, num_points=1024, iters=3, n_pairs=48),
+}
+
+
+def make_headline(ref=None, which=("cfg1", "cfg2"), threads=1):
+    """The benchmark's own configurations pinned from the LIVE reference: the reference's ``test_one_epoch``
+    (model/vcrnet_model.py:521-649, run on the host through ref_harness.cpu_mode) over the 48-item synthetic test partition,
+    in fp32 (the pin) and again with the network and inputs in fp64 (``net.double()``: the same reference code, a numerical
+    yardstick for how far fp32 rounding alone moves each pair).  Stored per config: R/t of every pair (fp32 + fp64), the
+    first batch's srcK / src_corrK, and the aggregate metrics testVCRNet prints."""
+    torch.set_num_threads(threads)
+    ref = ref or ref_harness.import_reference()
+    VM = ref.vcrnet_model
+    lpd = dict(np.load(os.path.join(GOLD, "lpd_pretrained_weights.npz")))
+    sd_t = synth.checkpoint_to_torch(synth.make_checkpoint(1234, emb_weights=lpd))
+    for name in which:
+        c = HEADLINE[name]
+        ov2 = OV2 if c["partial"] else 0.75
+        args = ref_harness.default_args(partial=c["partial"], overlap2=ov2, iter=c["iters"], num_points=c["num_points"])
+        p = synth.make_pairs(c["n_pairs"], c["num_points"], partial=c["partial"])
+        out = {}
+        for tag, dt in (("", torch.float32), ("64", torch.float64)):
+            net = VM.VCRNet(args).eval()
+            net.load_state_dict(sd_t, strict=True)
+            loader = _loader_from_pairs(p, c["batch"])
+            if dt == torch.float64:
+                net = net.double()
+                loader = [tuple(x.double() if x.is_floating_point() else x for x in b) for b in loader]
+            with ref_harness.cpu_mode(), torch.no_grad():
+                res = VM.test_one_epoch(args, net, loader)
+                first = VM.vcrnetIter(net, loader[0][0], loader[0][1], iter=c["iters"])
+                it1 = VM.vcrnetIter(net, loader[0][0], loader[0][1], iter=1) if c["iters"] > 1 else None
+            m = aggregate_metrics(ref, res)
+            out.update({f"R_ab{tag}": res[8], f"t_ab{tag}": res[9], f"R_ba{tag}": res[12], f"t_ba{tag}": res[13],
+                        f"srcK{tag}": N_(first[0]), f"corrK{tag}": N_(first[1])})
+            if it1 is not None:      # first refinement iteration of the first batch: srcK are ORIGINAL source points, so the
+                out.update({f"srcK_it1{tag}": N_(it1[0]), f"corrK_it1{tag}": N_(it1[1]),       # selections compare as sets
+                            f"R_ab_it1{tag}": N_(it1[2]), f"t_ab_it1{tag}": N_(it1[3])})
+            out.update({f"m{tag}.{k}": np.float64(v) for k, v in m.items()})
+            print(name, tag or "32", {k: float(f"{v:.6g}") for k, v in m.items()})
+        d = np.abs(out["R_ab"] - out["R_ab64"]).reshape(c["n_pairs"], -1).max(1)
+        print(name, "fp32 vs fp64 reference: max|dR| per pair: median %.3g max %.3g" % (np.median(d), d.max()))
+        save("headline_" + name, R_gt=p["R_ab"], t_gt=p["t_ab"], euler_gt=p["euler_ab"], overlap2=np.array(ov2),
+             batch=np.array(c["batch"]), iters=np.array(c["iters"]), num_points=np.array(c["num_points"]),
+             **out)
+
+
+def make_identity(ref=None):
+    """--pointer identity (model/vcrnet_model.py:477-478, 502-505): Identity returns its inputs, so both embeddings are
+    doubled before the head.  Whole-to-whole, 2 pairs x 256 points, from the live reference."""
+    torch.set_num_threads(1)
+    ref = ref or ref_harness.import_reference()
+    VM = ref.vcrnet_model
+    lpd = dict(np.load(os.path.join(GOLD, "lpd_pretrained_weights.npz")))
+    sd_t = synth.checkpoint_to_torch(synth.make_checkpoint(1234, emb_weights=lpd))
+    net = VM.VCRNet(ref_harness.default_args(pointer="identity")).eval()
+    missing = net.load_state_dict(sd_t, strict=False)
+    assert not missing.missing_keys, missing
+    p = synth.make_pairs(2, 256, first_item=150)
+    with torch.no_grad():
+        o = VM.vcrnetIter(net, T(p["src"]), T(p["tgt"]), iter=1)
+    save("vcrnet_identity_pointer", src=p["src"], tgt=p["tgt"], corrK=N_(o[1]), R_ab=N_(o[2]), t_ab=N_(o[3]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         make_variants()
@@ -353,6 +452,10 @@ if __name__ == "__main__":
         make_tnet()
     elif len(sys.argv) > 1 and sys.argv[1] == "ragged":
         make_ragged()
+    elif len(sys.argv) > 1 and sys.argv[1] == "identity":
+        make_identity()
+    elif len(sys.argv) > 1 and sys.argv[1] == "headline":
+        make_headline(which=tuple(sys.argv[2:]) or ("cfg1", "cfg2"))
     elif len(sys.argv) > 1 and sys.argv[1] == "lpd_train":
         make_lpd_train()
     else:

@@ -440,6 +440,8 @@ def vcrnet_forward(p, src, tgt, partial=False, overlap2=0.75, h=4, pointer="tran
     if pointer == "transformer":
         sp, tp = transformer_forward(p, se, te, h=h, partial=partial, overlap2=overlap2)  # :503
         se, te = (se + sp).astype(F32), (te + tp).astype(F32)                           # :504-505
+    elif pointer == "identity":                                                         # Identity returns its inputs (:65)
+        se, te = (se + se).astype(F32), (te + te).astype(F32)                           # :504-505
     stages.update(src_emb=se, tgt_emb=te)
     sK, cK = vcp_topk_forward(se, te, src, tgt, partial=partial, overlap2=overlap2)     # :507
     R, t = svd_head(sK, cK, p.get("svd.reflect"))                                       # :509

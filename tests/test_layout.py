@@ -156,3 +156,47 @@ def test_every_entry_point_rejects_null_arguments():
         assert isinstance(rc, int) and rc < 0, (name, rc)
         checked += 1
     assert checked >= 50
+
+
+def _cpu_replicate(module):
+    """What torch.nn.parallel.replicate() does to a module tree, on the CPU: shallow __dict__ copies flagged _is_replica, with
+    empty _parameters and the (broadcast) parameter copies set as plain tensor attributes."""
+    import torch
+    mods = list(module.modules())
+    idx = {m: i for i, m in enumerate(mods)}
+    reps = [m._replicate_for_data_parallel() for m in mods]
+    for m, r in zip(mods, reps):
+        for key, child in m._modules.items():
+            r._modules[key] = None if child is None else reps[idx[child]]
+        for key, p in m._parameters.items():
+            if p is not None:
+                c = p.detach().clone()
+                c.requires_grad_(p.requires_grad)
+                setattr(r, key, c * 1.0 if p.requires_grad else c)       # non-leaf copy, like Broadcast's outputs
+    return reps[0]
+
+
+def test_dataparallel_replica_code_paths():
+    """inside nn.DataParallel replicas parameters() is empty and __dict__ is a shallow copy of the original's.
+    The LPD training-mode test and the 12 trainable tensors must come from the conv attributes, and the packed-weight cache
+    of a replica must be its own dict, not the original's (shared by every replica thread)."""
+    import torch
+    import vcr_net_b200 as V
+    from vcr_net_b200 import functional as Fn
+    from oracle.ref_harness import default_args
+    net = V.LPDNet(default_args(), negative_slope=0.2)
+    Fn.packed(net, "probe", [net.conv1_lpd.weight], lambda: "original")
+    rep = _cpu_replicate(net)
+    assert list(rep.parameters()) == [] and rep._is_replica
+    ts = Fn.lpdnet_param_tensors(rep)
+    assert len(ts) == 12 and all(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+    assert [tuple(t.shape) for t in ts] == [tuple(dict(net.named_parameters())[n].shape) for n in Fn.LPDNET_PARAM_ORDER]
+    assert rep.__dict__["_vcr_packed"] is net.__dict__["_vcr_packed"]          # the shared dict the replica must not use
+    calls = []
+    v1 = Fn.packed(rep, "probe", [rep.conv1_lpd.weight], lambda: calls.append(1) or "replica")
+    v2 = Fn.packed(rep, "probe", [rep.conv1_lpd.weight], lambda: calls.append(1) or "replica")
+    assert v1 == v2 == "replica" and len(calls) == 1                           # cached for the replica's lifetime ...
+    assert net.__dict__["_vcr_packed"]["probe"][1] == "original"               # ... without touching the original's cache
+    assert "_vcr_packed_replica" not in net.__dict__
+    rep2 = _cpu_replicate(net)                                                  # the next forward's replica starts clean
+    assert "_vcr_packed_replica" not in rep2.__dict__

@@ -13,10 +13,16 @@ precision = os.environ.get("VCR_PRECISION", "h3")
 VALID = ("fp32", "h3", "fp16", "bf16")
 # flash attention kernel (attn_tc.cu) vs materialised scores through the GEMM kernel (tensor-core modes only)
 flash_attention = os.environ.get("VCR_FLASH", "1") != "0"
-# vcrnetIter: compute the loop-invariant target embedding emb_nn(tgt) once per call instead of once per --iter iteration
-# (bit-identical outputs).  Off by default so the default path does exactly the work the reference does per iteration;
-# bench.py reports the throughput with the switch on as a separate, labelled field.
-reuse_target_embedding = os.environ.get("VCR_REUSE_TGT_EMB", "0") == "1"
+# vcrnetIter (--iter > 1): what is hoisted out of the refinement loop.  The target cloud never changes inside the loop
+# (model/vcrnet_model.py:24-28), so emb_nn(tgt), encoder(tgt_emb) with its K / V projections in the decoder's src_attn, and
+# the decoder's first self-attention sublayer on tgt are loop-invariant (functional.TargetInvariants).  Outputs are
+# bit-identical at every level (tests/test_gpu_parity.py::test_vcrnet_iter_hoisting_is_bit_identical):
+#   "all" (default)  everything above, computed once per call
+#   "emb"            only emb_nn(tgt)
+#   "none"           recompute everything every iteration, exactly the work the reference does (bench.py reports this as
+#                    the labelled variant `variant_no_hoisting`)
+hoist = os.environ.get("VCR_HOIST", "all")
+assert hoist in ("all", "emb", "none"), hoist
 
 
 # feature-space kNN (16 <= D <= 128): tcgen05 prefilter + exact re-rank (csrc/knn.cu, bit-identical indices).
@@ -68,5 +74,12 @@ flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "2"))
 
 
 # vcrnetIter: serve repeated calls of one (network, shapes, iter) from a captured CUDA graph (vcr_net_b200/graph.py;
-# bit-identical outputs, fresh result tensors).  Off by default: the headline numbers go through the eager module API.
-cuda_graph = os.environ.get("VCR_CUDA_GRAPH", "0") == "1"
+# bit-identical outputs, fresh result tensors).  ON by default for eval-mode VCRNet: the first call of a
+# shape runs eagerly, the second captures, later ones replay -- one graph launch instead of ~150 Python -> ctypes -> launch
+# round trips per call.  VCR_CUDA_GRAPH=0 keeps every call on the eager path (bench.py reports that as `variant_eager`).
+cuda_graph = os.environ.get("VCR_CUDA_GRAPH", "1") == "1"
+
+def graph_key():
+    """Every switch that changes which kernels a captured vcrnetIter graph contains."""
+    return (precision, hoist, flash_attention, fused_softcorr, fused_key_stat, str(knn_tc),
+            str(gemm_pair), int(flash_warps))

@@ -16,6 +16,7 @@
 // each product is hi*hi + 2^-11 (hi*lo + lo*hi) with main and correction terms in separate TMEM
 // accumulators (see gemm_tc.cu).  NTERMS = 1: single fp16 / bf16 pass.
 // Optional key mask keep[B,Nk] (partial overlap, model/transformer.py:48-52): masked keys get -1e9.
+#include <atomic>
 #include "tc_common.cuh"
 
 namespace {
@@ -463,14 +464,12 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 }  // namespace
 
-static int g_vcr_flash_warps = 2;
+static std::atomic<int> g_vcr_flash_warps{2};      // tuning knob (see vcr_set_flash_warps)
 
 // Softmax warps per TMEM lane quarter of the flash attention kernel: 2 (8 softmax warps, 384 threads) or 4 (16 warps,
 // 640 threads).  Process-wide; returns the previous setting.  Results agree to fp32 rounding of the row sums.
 VCR_API int vcr_set_flash_warps(int nwq) {
-    const int old = g_vcr_flash_warps;
-    g_vcr_flash_warps = nwq == 4 ? 4 : 2;
-    return old;
+    return g_vcr_flash_warps.exchange(nwq == 4 ? 4 : 2);
 }
 
 // Q: operand buffer [planes][B*Nq][ldq], head hh in columns [hh*128, hh*128+128) of the given base;
@@ -497,7 +496,7 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
     p.scale_log2 = scale * kLog2e; p.keep = keep;
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
-    if (g_vcr_flash_warps == 4) {
+    if (g_vcr_flash_warps.load(std::memory_order_relaxed) == 4) {
         if (mode == 0) return launch_attn<3, 0, 4>(tq, tk, tv, p, stream);
         if (mode == 1) return launch_attn<1, 0, 4>(tq, tk, tv, p, stream);
         return launch_attn<1, 1, 4>(tq, tk, tv, p, stream);

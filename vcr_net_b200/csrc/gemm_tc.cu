@@ -21,6 +21,7 @@
 //   - operand-format TRANSPOSED output for columns >= h_split (V^T for attention: with one TMEM lane
 //     = one row per thread the transposed store is the coalesced one).
 // so consecutive GEMMs never round-trip through a separate conversion kernel.
+#include <atomic>
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -471,14 +472,14 @@ int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmP
     using C_ = Cfg<3, 2>;
     constexpr int CL = 2 * MC;
     auto kern = gemm_tc_kernel<3, 0, 2, MC>;
-    // per device (nn.DataParallel drives several devices from one process): the function attribute and the number of
-    // co-schedulable clusters; idempotent, benign race
-    static int max_clusters_dev[64];
-    static bool known[64];
+    // per device (nn.DataParallel drives several devices from one process, one thread each): the function attribute and the
+    // number of co-schedulable clusters.  Published with release/acquire: a thread either sees the final value or
+    // recomputes the same one (the probe is idempotent), never a half-written slot.
+    static std::atomic<int> max_clusters_dev[64];     // 0 = unknown, n + 1 = n clusters
     int dev = 0;
     cudaGetDevice(&dev);
     const int slot = dev & 63;
-    if (!known[slot]) {
+    if (max_clusters_dev[slot].load(std::memory_order_acquire) == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) != cudaSuccess)
             return VCR_ERR_LAUNCH;
         cudaLaunchConfig_t q = {};
@@ -489,10 +490,9 @@ int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmP
         q.attrs = at; q.numAttrs = 1;
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        max_clusters_dev[slot] = n;
-        known[slot] = true;
+        max_clusters_dev[slot].store(n + 1, std::memory_order_release);
     }
-    const int max_clusters = max_clusters_dev[slot];
+    const int max_clusters = max_clusters_dev[slot].load(std::memory_order_acquire) - 1;
     if (max_clusters < 1) return VCR_ERR_UNSUPPORTED;
     const long long units = (long long)vcr_cdiv(p.M, 2 * BM) * vcr_cdiv(vcr_cdiv(p.N, BN), MC) * p.nb_outer * p.nb_inner;
     const int clusters = (int)(units < max_clusters ? units : max_clusters);
@@ -542,16 +542,18 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcGemmParams
 
 }  // namespace
 
-static int g_vcr_gemm_pair = 2;      // 0: never, 1: always, 2: auto (see vcr_set_gemm_pair)
+static std::atomic<int> g_vcr_gemm_pair{2};      // tuning knob, 0: never, 1: always, 2: auto (see vcr_set_gemm_pair)
 
 vcr_tmap_encode_fn vcr_get_tmap_encoder() {
-    static vcr_tmap_encode_fn fn = nullptr;
+    static std::atomic<vcr_tmap_encode_fn> cached{nullptr};      // idempotent lookup, published atomically
+    vcr_tmap_encode_fn fn = cached.load(std::memory_order_acquire);
     if (!fn) {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<vcr_tmap_encode_fn>(ptr);
+        cached.store(fn, std::memory_order_release);
     }
     return fn;
 }
@@ -610,7 +612,7 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
     p.out_planes = out_planes; p.out_bf16 = mode == 2;
     // auto: pairs everywhere except the residual epilogue at K < 1024, the one shape class where the pair measured slower
     // (0.94-0.97x; 1.03-1.12x elsewhere, scripts/pair_diag.py on B200)
-    const int pol = g_vcr_gemm_pair;
+    const int pol = g_vcr_gemm_pair.load(std::memory_order_relaxed);
     if (mode == 0 && pol == 3) {
         // two pairs per cluster, A multicast: both CTAs of a pair fetch 64-row boxes of A and of B
         CUtensorMap tmA2, tmB2;
@@ -640,9 +642,7 @@ VCR_API int vcr_gemm_tc(const void* A, int lda, long long a_rows_total, int a_co
 VCR_API int vcr_gemm_quad_clusters(void) { return quad_clusters(); }
 
 VCR_API int vcr_set_gemm_pair(int on) {
-    const int old = g_vcr_gemm_pair;
-    g_vcr_gemm_pair = on < 0 ? 0 : (on > 3 ? 2 : on);
-    return old;
+    return g_vcr_gemm_pair.exchange(on < 0 ? 0 : (on > 3 ? 2 : on));
 }
 
 // fp32 [rows, cols] (row stride ld) -> operand format [planes][rows][ldo] (fp16, or bf16 when bf16 != 0)

@@ -21,6 +21,7 @@
 // Roofline: bytes = 4*D*N in + 4*k*N out per cloud (candidate chunks are re-read from L2 by the N/32
 // CTAs of a cloud), flops = 2*D*N^2 (+ ~N^2 select steps): FP32-FMA bound at D = 64, selection
 // (issue) bound at D = 3 -- DESIGN.md section 4.
+#include <atomic>
 #include "tc_common.cuh"
 
 namespace {
@@ -799,13 +800,11 @@ VCR_API size_t vcr_knn_workspace_bytes(int B, int N) { return (size_t)B * N * si
 // x: [B,D,N] (token_major=0, the reference layout) or [B,N,D] (token_major=1); idx: [B,N,k].
 // Either idx32 or idx64 (or both) may be given.  Requires 1 <= k <= 31, N >= k+1; any D >= 1 (D <= 4 is staged
 // 4 dims at a time, wider features 16 dims at a time).
-static int g_vcr_knn3_direct = 1;
+static std::atomic<int> g_vcr_knn3_direct{1};      // tuning knob (see vcr_set_knn3_direct)
 
 // D == 3: distances on the fly (knn3_kernel, default) or the generic tile kernel.  Same indices; returns the previous setting.
 VCR_API int vcr_set_knn3_direct(int on) {
-    const int old = g_vcr_knn3_direct;
-    g_vcr_knn3_direct = on ? 1 : 0;
-    return old;
+    return g_vcr_knn3_direct.exchange(on ? 1 : 0);
 }
 
 VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
@@ -819,7 +818,7 @@ VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_m
     else knn_sqnorm_kernel<false><<<g, 256, 0, stream>>>(x, D, N, xx);
     VCR_CHECK_LAUNCH();
     if (k > 31) return VCR_ERR_UNSUPPORTED;
-    if (D == 3 && g_vcr_knn3_direct) {
+    if (D == 3 && g_vcr_knn3_direct.load(std::memory_order_relaxed)) {
         dim3 grid(vcr_cdiv(N, TQ3), B);
         if (token_major) knn3_kernel<true><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);
         else knn3_kernel<false><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);

@@ -28,7 +28,14 @@ def _versions(params):
 
 
 def packed(module, key, params, build):
-    cache = module.__dict__.setdefault("_vcr_packed", {})
+    """Packed-weight cache on the module, keyed by (data_ptr, _version) of the source tensors.
+
+    nn.DataParallel: ``replicate()`` shallow-copies ``__dict__`` on every forward, so the original's cache dict would be
+    SHARED by the per-device replica threads and keyed by freshly broadcast weight copies whose addresses are recycled from
+    call to call (a stale hit after an optimizer step).  Replicas therefore use a dict of their own, created on the replica
+    (its ``__dict__`` is a private copy), which lives exactly as long as the replica: one forward."""
+    d = module.__dict__
+    cache = d.setdefault("_vcr_packed_replica", {}) if d.get("_is_replica", False) else d.setdefault("_vcr_packed", {})
     ver = _versions(params)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
@@ -74,7 +81,7 @@ def lpdnet_weights(m):
     return packed(m, "lpdnet", params, build)
 
 
-def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None):
+def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None, out=None):
     """xyz [B,3,N] -> embedding tokens [B,N,emb_dims]  (model/lpdnet_model.py:103-137, incl. the optional t3d / tfea
     TranformNets, eval mode).
 
@@ -126,10 +133,10 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
     ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_xyz, slope, cat[:, :, 256:512])  # :130-132
     mode = config.precision
     if mode == "fp32":
-        emb = ops.gemm(cat, W["w3"], W["b3"], act=1, slope=slope)            # :134-135
+        emb = ops.gemm(cat, W["w3"], W["b3"], act=1, slope=slope, out=out)   # :134-135
     else:
         w3 = packed(m, "w3_" + mode, [m.conv3_lpd.weight], lambda: ops.to_operand(W["w3"], mode))
-        emb = torch.empty((B, N, W["w3"].shape[0]), dtype=_F32, device=xyz.device)
+        emb = out if out is not None else torch.empty((B, N, W["w3"].shape[0]), dtype=_F32, device=xyz.device)
         ops.gemm_tc(ops.to_operand(cat, mode), w3, B * N, W["w3"].shape[0], 512, bias=W["b3"], act=1,
                     slope=slope, c=emb)
     if stages is not None:
@@ -205,13 +212,13 @@ class LPDNetTrainFn(torch.autograd.Function):
             xyz_t = ops.transpose_batched(xyz.contiguous())                  # [B,N,3]
         ctx.m = m
         ctx.st = st
-        ctx.saved = (xyz_t, emb)
+        ctx.save_for_backward(xyz_t, emb)          # outputs are allowed here; no output -> grad_fn -> ctx -> output cycle
         return emb
 
     @staticmethod
     def backward(ctx, g_emb):
         m, st = ctx.m, ctx.st
-        xyz_t, emb = ctx.saved
+        xyz_t, emb = ctx.saved_tensors
         W = lpdnet_weights(m)
         slope = float(m.negative_slope)
         k = m.k
@@ -288,10 +295,21 @@ LPDNET_PARAM_ORDER = ("conv1_lpd.weight", "conv1_lpd.bias", "conv2_lpd.weight", 
                       "convDG2.0.weight", "convDG2.0.bias", "convSN1.0.weight", "convSN1.0.bias")
 
 
+def lpdnet_param_tensors(m):
+    """The 12 trainable tensors in LPDNET_PARAM_ORDER, read from the conv ATTRIBUTES: inside an nn.DataParallel replica
+    ``parameters()`` / ``named_parameters()`` are empty (the broadcast copies are plain attributes, torch replicate())."""
+    out = []
+    for name in LPDNET_PARAM_ORDER:
+        obj = m
+        for part in name.split("."):
+            obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+        out.append(obj)
+    return out
+
+
 def lpdnet_tokens_train(m, xyz, idx_feat=None, idx_xyz=None):
     """Differentiable lpdnet_tokens (w.r.t. the module's parameters)."""
-    named = dict(m.named_parameters())
-    return LPDNetTrainFn.apply(m, xyz, idx_feat, idx_xyz, *[named[n] for n in LPDNET_PARAM_ORDER])
+    return LPDNetTrainFn.apply(m, xyz, idx_feat, idx_xyz, *lpdnet_param_tensors(m))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -486,33 +504,49 @@ def mha_weights_tc(m, mode):
         "wkv": ops.to_operand(W["wkv"], mode), "wo": ops.to_operand(W["wo"], mode)})
 
 
-def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
-    """MultiHeadedAttention.forward (model/transformer.py:202-224) on tensor cores.
+def mha_project_self(m, x_op, B, N, mode, dev, qk=None, vt=None):
+    """Self-attention projections: one fused QKV GEMM writing Q | K row-major and V TRANSPOSED per head, all in operand
+    format, straight from the epilogue.  qk / vt: optional destination views (rows of a larger buffer)."""
+    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+    D = m.h * m.d_k
+    if qk is None:
+        qk = ops.Operand.empty(B * N, 2 * D, mode, dev)
+    if vt is None:
+        vt = ops.Operand.empty(B * D, N, mode, dev)                      # rows (b, head*dk + d), cols = keys
+    ops.gemm_tc(x_op, Wt["wqkv"], N, 3 * D, D, nbo=B, a_off=(N, 0, 0, 0), bias=W["bqkv"],
+                h=qk, h_strides=(N * qk.ld, 0), h_split=2 * D, ht=vt, ht_strides=(D * vt.ld, 0))
+    return qk.cols_view(0, D), qk.cols_view(D, D), vt
 
-    xq_op / xkv_op: operand-format LayerNorm outputs [B*N, D] (xkv_op None => self-attention).
-    Projections write Q, K row-major and V TRANSPOSED per head in operand format straight from the
-    GEMM epilogue; scores are one batched GEMM over (batch, head) addressed by row/column offsets."""
+
+def mha_project_q(m, xq_op, rows, mode, dev, out=None):
+    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+    D = m.h * m.d_k
+    q_v = out if out is not None else ops.Operand.empty(rows, D, mode, dev)
+    ops.gemm_tc(xq_op, Wt["wq"], rows, D, D, bias=W["bq"], h=q_v, h_split=D)
+    return q_v
+
+
+def mha_project_kv(m, xkv_op, B, Nk, mode, dev, k_out=None, vt_out=None):
+    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+    D = m.h * m.d_k
+    k_v = k_out if k_out is not None else ops.Operand.empty(B * Nk, D, mode, dev)
+    vt = vt_out if vt_out is not None else ops.Operand.empty(B * D, Nk, mode, dev)
+    ops.gemm_tc(xkv_op, Wt["wkv"], Nk, 2 * D, D, nbo=B, a_off=(Nk, 0, 0, 0), bias=W["bkv"],
+                h=k_v, h_strides=(Nk * k_v.ld, 0), h_split=D, ht=vt, ht_strides=(D * vt.ld, 0))
+    return k_v, vt
+
+
+def mha_attend(m, q_v, k_v, vt, B, Nq, Nk, residual, mode, out=None, max_ws_bytes=3 << 30):
+    """softmax(QK^T/sqrt(d_k)) V (+ the partial-overlap key selection, model/transformer.py:29-55), merge heads,
+    linears[3] + residual (:220-224).  q_v / k_v / vt: operand-format projections of B batch items."""
     W, Wt = mha_weights(m), mha_weights_tc(m, mode)
     D, h, dk = m.h * m.d_k, m.h, m.d_k
     dev = residual.device
     scale = 1.0 / math.sqrt(dk)
-    vt = ops.Operand.empty(B * D, Nk, mode, dev)                         # rows (b, head*dk + d), cols = keys
-    if xkv_op is None:
-        qk = ops.Operand.empty(B * Nq, 2 * D, mode, dev)
-        ops.gemm_tc(xq_op, Wt["wqkv"], Nq, 3 * D, D, nbo=B, a_off=(Nq, 0, 0, 0), bias=W["bqkv"],
-                    h=qk, h_strides=(Nq * qk.ld, 0), h_split=2 * D, ht=vt, ht_strides=(D * vt.ld, 0))
-        q_v, k_v = qk.cols_view(0, D), qk.cols_view(D, D)
-    else:
-        q_v = ops.Operand.empty(B * Nq, D, mode, dev)
-        ops.gemm_tc(xq_op, Wt["wq"], B * Nq, D, D, bias=W["bq"], h=q_v, h_split=D)
-        k_v = ops.Operand.empty(B * Nk, D, mode, dev)
-        ops.gemm_tc(xkv_op, Wt["wkv"], Nk, 2 * D, D, nbo=B, a_off=(Nk, 0, 0, 0), bias=W["bkv"],
-                    h=k_v, h_strides=(Nk * k_v.ld, 0), h_split=D, ht=vt, ht_strides=(D * vt.ld, 0))
     att = ops.Operand.empty(B * Nq, D, mode, dev)
     keep = None
     if m.is_src:
         # partial overlap (:35-53): column sums of the unmasked probabilities pick the surviving keys.
-        # This one statistic still goes through materialised scores (chunked); the attention itself is flash.
         if dk == 128 and mode == "h3" and config.fused_key_stat:
             # two tcgen05 sweeps per (batch, head, query tile): no score matrix in HBM (csrc/attn_colsum_tc.cu)
             csum = ops.attn_colsum_tc(q_v, k_v, B, h, Nq, Nk, dk, scale)
@@ -543,9 +577,40 @@ def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30):
                                     keep=keep[b0:b0 + nb] if keep is not None else None, rows_per_batch=h * Nq)
             ops.gemm_tc(P, vt.rows_view(b0 * D, nb * D), Nq, dk, Nk, nbo=nb, nbi=h, a_off=(h * Nq, Nq, 0, 0),
                         b_off=(D, dk, 0, 0), h=att.rows_view(b0 * Nq, nb * Nq), h_strides=(Nq * att.ld, dk), h_split=dk)
-    out = torch.empty((B, Nq, D), dtype=_F32, device=dev)
+    if out is None:
+        out = torch.empty((B, Nq, D), dtype=_F32, device=dev)
     ops.gemm_tc(att, Wt["wo"], B * Nq, D, D, bias=W["bo"], c=out, residual=residual)
+    if m.__dict__.get("record_attn", False):
+        m.attn = attn_probs_head_sum(q_v, k_v, B, h, Nq, Nk, dk, scale, keep)
     return out
+
+
+def attn_probs_head_sum(q_v, k_v, B, h, Nq, Nk, dk, scale, keep):
+    """``MultiHeadedAttention.attn`` (model/transformer.py:216-219): the probabilities summed over the heads, [B, Nq, Nk],
+    what util/util.py:31-44 plots.  OPT-IN (``module.record_attn = True``): it is the one O(N^2) tensor of the path that
+    the flash kernel exists to avoid, so it is materialised through the score GEMM + softmax only on request."""
+    dev = q_v.buf.device
+    ldS = (Nk + 3) // 4 * 4
+    S = torch.empty((B, h, Nq, ldS), dtype=_F32, device=dev)
+    ops.gemm_tc(q_v, k_v, Nq, Nk, dk, nbo=B, nbi=h, a_off=(Nq, 0, 0, dk), b_off=(Nk, 0, 0, dk), alpha=scale, c=S,
+                c_strides=(h * Nq * ldS, Nq * ldS))
+    ops.softmax_rows_(S.view(B * h * Nq, ldS)[:, :Nk], keep, h * Nq)
+    return S[..., :Nk].sum(dim=1)
+
+
+def mha_tc(m, xq_op, xkv_op, B, Nq, Nk, residual, mode, max_ws_bytes=3 << 30, out=None):
+    """MultiHeadedAttention.forward (model/transformer.py:202-224) on tensor cores.
+
+    xq_op / xkv_op: operand-format LayerNorm outputs [B*N, D] (xkv_op None => self-attention).
+    Projections write Q, K row-major and V TRANSPOSED per head in operand format straight from the
+    GEMM epilogue; attention is the flash kernel over (batch, head) addressed by row/column offsets."""
+    dev = residual.device
+    if xkv_op is None:
+        q_v, k_v, vt = mha_project_self(m, xq_op, B, Nq, mode, dev)
+    else:
+        q_v = mha_project_q(m, xq_op, B * Nq, mode, dev)
+        k_v, vt = mha_project_kv(m, xkv_op, B, Nk, mode, dev)
+    return mha_attend(m, q_v, k_v, vt, B, Nq, Nk, residual, mode, out=out, max_ws_bytes=max_ws_bytes)
 
 
 def ffn_tc(m, n_op, rows, residual, mode):
@@ -598,6 +663,109 @@ def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False, wa
         nrm = model.decoder.norm
         return ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=final_residual)
     return _ln(model.decoder.norm, y, residual=final_residual)
+
+
+class TargetInvariants:
+    """Everything of one ``vcrnetIter`` call that depends on the TARGET cloud only (model/vcrnet_model.py:24-28: the loop
+    transforms ``src`` and re-runs the network, ``tgt`` never changes), computed once per call instead of once per
+    iteration as the reference does:
+
+      * ``emb_nn(tgt)``                                                   (model/vcrnet_model.py:500)
+      * ``encoder(tgt_emb)`` -- the memory of the ``src_p = model(tgt, src)`` direction (model/transformer.py:270) --
+        and its K / V^T projections in every decoder layer's ``src_attn``
+      * decoder layer 0's self-attention sublayer on ``tgt`` and the Q projection of the next sublayer
+        (the ``tgt_p = model(src, tgt)`` direction, model/transformer.py:180-183)
+
+    The per-iteration kernels read these through COMBINED 2B-item buffers ([src half | tgt half]) whose invariant half is
+    written once here and whose other half is rewritten each iteration in place, so nothing is copied.  Every kernel on
+    the path computes a batch item independently of its neighbours, hence outputs are bit-identical to the non-hoisted
+    path (tests/test_gpu_parity.py::test_vcrnet_iter_hoisting_is_bit_identical)."""
+
+    def __init__(self, net, tgt: torch.Tensor):
+        tr = net.pointer
+        model = tr.model
+        mode = config.precision
+        B, _, N = tgt.shape
+        dev = tgt.device
+        D = tr.emb_dims
+        self.B, self.N, self.D, self.mode = B, N, D, mode
+        self.emb2 = torch.empty((2 * B, N, D), dtype=_F32, device=dev)         # [emb(src) | emb(tgt)]
+        emb_tokens(net.emb_nn, tgt, out=self.emb2[B:])
+        tgt_tok = self.emb2[B:]
+        # encoder(tgt): memory of the decoder items that hold src
+        x = tgt_tok
+        for layer in model.encoder.layers:
+            x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
+            x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * N, x, mode)
+        mem_t = _ln_op(model.encoder.norm, x, mode)
+        self.k2, self.vt2 = [], []                                             # per decoder layer: [from enc(tgt) | from enc(src)]
+        for layer in model.decoder.layers:
+            k2 = ops.Operand.empty(2 * B * N, D, mode, dev)
+            vt2 = ops.Operand.empty(2 * B * D, N, mode, dev)
+            mha_project_kv(layer.src_attn, mem_t, B, N, mode, dev, k_out=k2.rows_view(0, B * N), vt_out=vt2.rows_view(0, B * D))
+            self.k2.append(k2); self.vt2.append(vt2)
+        # decoder layer 0, sublayer 0 on tgt, and the query projection of sublayer 1
+        l0 = model.decoder.layers[0]
+        self.y1 = torch.empty((2 * B, N, D), dtype=_F32, device=dev)           # [y1(src) | y1(tgt)]
+        mha_tc(l0.self_attn, _ln_op(l0.sublayer[0].norm, tgt_tok, mode), None, B, N, N, tgt_tok, mode, out=self.y1[B:])
+        self.q2 = ops.Operand.empty(2 * B * N, D, mode, dev)                   # [Q(src) | Q(tgt)]
+        mha_project_q(l0.src_attn, _ln_op(l0.sublayer[1].norm, self.y1[B:], mode), B * N, mode, dev,
+                      out=self.q2.rows_view(B * N, B * N))
+
+    @staticmethod
+    def supported(net, src, tgt) -> bool:
+        from .model.transformer import Transformer
+        return (config.precision != "fp32" and isinstance(net.pointer, Transformer) and src.shape == tgt.shape
+                and len(net.pointer.model.decoder.layers) >= 1)
+
+
+def emb_tokens(emb_nn, xyz, out=None):
+    """emb_nn.forward_tokens, written into ``out`` when given (LPDNet writes there directly, the other embeddings copy)."""
+    from .model.lpdnet_model import LPDNet
+    if out is None:
+        return emb_nn.forward_tokens(xyz)
+    if isinstance(emb_nn, LPDNet) and not torch.is_grad_enabled():
+        return lpdnet_tokens(emb_nn, xyz, out=out)
+    out.copy_(emb_nn.forward_tokens(xyz))
+    return out
+
+
+def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False):
+    """One refinement iteration of Transformer.forward + the VCRNet residual (model/transformer.py:264-272,
+    model/vcrnet_model.py:504-505) given the target-side invariants; ``inv.emb2[:B]`` holds this iteration's emb(src).
+    Returns what transformer_tokens(add_input=True) returns."""
+    model, mode = tr.model, inv.mode
+    B, N, D = inv.B, inv.N, inv.D
+    dev = inv.emb2.device
+    src_tok = inv.emb2[:B]
+    # encoder(src): memory of the decoder items that hold tgt
+    x = src_tok
+    for layer in model.encoder.layers:
+        x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
+        x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * N, x, mode)
+    mem_s = _ln_op(model.encoder.norm, x, mode)
+    y = None
+    for li, layer in enumerate(model.decoder.layers):
+        k2, vt2 = inv.k2[li], inv.vt2[li]
+        mha_project_kv(layer.src_attn, mem_s, B, N, mode, dev, k_out=k2.rows_view(B * N, B * N), vt_out=vt2.rows_view(B * D, B * D))
+        if li == 0:
+            mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, src_tok, mode), None, B, N, N, src_tok, mode, out=inv.y1[:B])
+            y = inv.y1
+            mha_project_q(layer.src_attn, _ln_op(layer.sublayer[1].norm, y[:B], mode), B * N, mode, dev,
+                          out=inv.q2.rows_view(0, B * N))
+            q2 = inv.q2
+        else:
+            y = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, y, mode), None, 2 * B, N, N, y, mode)
+            q2 = mha_project_q(layer.src_attn, _ln_op(layer.sublayer[1].norm, y, mode), 2 * B * N, mode, dev)
+        y = mha_attend(layer.src_attn, q2, k2, vt2, 2 * B, N, N, y, mode)
+        y = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[2].norm, y, mode), 2 * B * N, y, mode)
+    nrm = model.decoder.norm
+    if want_head:
+        out, op, sq = ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=inv.emb2)
+        pre = (HeadPre(op.rows_view(0, B * N), sq[:B]), HeadPre(op.rows_view(B * N, B * N), sq[B:]))
+        return out[:B], out[B:], pre
+    out = _ln(nrm, y, residual=inv.emb2)
+    return out[:B], out[B:]
 
 
 def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_input=False, want_head=False):

@@ -65,7 +65,8 @@ class LPDNet(nn.Module):
 
     def forward_tokens(self, x, idx_feat=None, idx_xyz=None, stages=None):
         """x [B,3,N] -> tokens [B,N,emb_dims] (internal fast path, no output transpose)."""
-        if stages is None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        # train-mode test on the conv attributes, not parameters(): replicas of nn.DataParallel have no parameters
+        if stages is None and torch.is_grad_enabled() and any(t.requires_grad for t in Fn.lpdnet_param_tensors(self)):
             if self.t3d or self.tfea:
                 raise Exception("Not implemented: backward through TranformNet (t3d/tfea); run under torch.no_grad()")
             return Fn.lpdnet_tokens_train(self, x, idx_feat=idx_feat, idx_xyz=idx_xyz)     # training: custom backward

@@ -13,15 +13,42 @@ from .transformer import Transformer
 
 
 def vcrnetIter(net, src, tgt, iter=1):
-    """model/vcrnet_model.py:21-43 with the reference's signature.  With ``config.cuda_graph`` (env VCR_CUDA_GRAPH=1, off
-    by default) repeated calls with the same network, shapes and ``iter`` are served by a captured CUDA graph
+    """model/vcrnet_model.py:21-43 with the reference's signature.
+
+    ``net`` may be the bare VCRNet or the ``nn.DataParallel`` wrapper the reference's bootstrap always applies
+    (util/initPara.py:260) and its loops pass in (model/vcrnet_model.py:561-563):
+      * one device: the wrapper would call ``net.module`` directly (torch DataParallel.forward), so it is unwrapped here and
+        the loop runs on the module -- with the loop-invariant hoisting and, when enabled, CUDA-graph replay;
+      * several devices: the batch is scattered ONCE and every replica runs the whole ``iter`` loop on its shard
+        (one replicate / scatter / gather per call instead of one per iteration); pairs are independent, so the gathered
+        result has the bits of the single-device loop.
+    With ``config.cuda_graph`` repeated calls with the same network, shapes and ``iter`` are served by a captured CUDA graph
     (vcr_net_b200/graph.py): the first call of a shape runs eagerly, the second captures, later ones replay; results are
-    fresh tensors and bit-identical to the eager loop; any in-place change of a parameter drops the cache."""
+    fresh tensors and bit-identical to the eager loop; any change of a parameter or buffer drops the cache."""
     from .. import config
+    if isinstance(net, nn.DataParallel) and isinstance(net.module, VCRNet) and src.is_cuda:
+        if len(net.device_ids) == 1 and src.device.index == net.device_ids[0]:
+            net = net.module
+        elif len(net.device_ids) > 1 and not (net.module.training and torch.is_grad_enabled()):
+            loop = nn.DataParallel(_IterLoop(net.module, int(iter)), device_ids=net.device_ids,
+                                   output_device=net.output_device, dim=net.dim)
+            return loop(src, tgt)
     if (config.cuda_graph and isinstance(net, VCRNet) and not net.training and src.is_cuda
-            and not torch.cuda.is_current_stream_capturing()):
+            and not torch.cuda.is_current_stream_capturing() and not net.__dict__.get("_is_replica", False)
+            and not any(m.__dict__.get("record_attn", False) for m in net.modules())):
         return _vcrnet_iter_cached(net, src, tgt, int(iter))
     return _vcrnet_iter_eager(net, src, tgt, iter)
+
+
+class _IterLoop(nn.Module):
+    """The refinement loop as a module, so that nn.DataParallel replicates / scatters once per vcrnetIter call."""
+
+    def __init__(self, net, iters):
+        super().__init__()
+        self.net, self.iters = net, iters
+
+    def forward(self, src, tgt):
+        return _vcrnet_iter_eager(self.net, src, tgt, self.iters)
 
 
 _GRAPH_CACHE_MAX = 4
@@ -30,11 +57,13 @@ _GRAPH_CACHE_MAX = 4
 def _vcrnet_iter_cached(net, src, tgt, iter):
     from .. import config
     from ..graph import GraphedRegistration
-    stamp = sum(p._version for p in net.parameters())
+    # every parameter AND buffer by (address, version): catches in-place updates, replaced tensors (.to() / .half() /
+    # load_state_dict(assign=True) / p.data = ...) and BatchNorm statistics
+    stamp = tuple((t.data_ptr(), t._version) for t in list(net.parameters()) + list(net.buffers()))
     cache = net.__dict__.setdefault("_vcr_graph_cache", {"stamp": stamp, "entries": {}})
     if cache["stamp"] != stamp:                       # weights were updated in place: captured pointers may be stale
         cache["stamp"], cache["entries"] = stamp, {}
-    key = (tuple(src.shape), tuple(tgt.shape), iter, str(src.device), config.precision, config.reuse_target_embedding)
+    key = (tuple(src.shape), tuple(tgt.shape), iter, str(src.device)) + config.graph_key()
     ent = cache["entries"].get(key)
     if ent is None:
         if len(cache["entries"]) >= _GRAPH_CACHE_MAX:
@@ -50,22 +79,24 @@ def _vcrnet_iter_cached(net, src, tgt, iter):
 def _vcrnet_iter_eager(net, src, tgt, iter=1):
     """model/vcrnet_model.py:21-43: refine `iter` times, composing R_f <- R_i R_f, t_f <- R_i t_f + t_i.
 
-    The target cloud never changes inside the loop, so its embedding ``emb_nn(tgt)`` is loop-invariant: with
-    ``config.reuse_target_embedding`` (default off) it is computed once per call and handed to every iteration instead of
-    being recomputed ``iter`` times as the reference does (:27).  Outputs are bit-identical either way."""
+    The target cloud never changes inside the loop, so with iter > 1 everything that depends on it alone
+    (functional.TargetInvariants: emb_nn(tgt), encoder(tgt_emb), the decoder's first self-attention sublayer on tgt and
+    the projections that read them) is computed once per call instead of ``iter`` times as the reference does (:27).
+    ``config.hoist`` = "all" (default) | "emb" | "none"; outputs are bit-identical at every level."""
     from .. import config
     transformed_src = src
     R_f = t_f = None
     srcK = src_corrK = None
-    tgt_tok = None
-    if iter > 1 and config.reuse_target_embedding and isinstance(net, VCRNet):
+    kw = {}
+    if iter > 1 and config.hoist != "none" and isinstance(net, VCRNet) and not (net.training and torch.is_grad_enabled()):
         with torch.no_grad():
-            tgt_tok = net.emb_nn.forward_tokens(tgt.contiguous())
+            tgt_c = tgt.contiguous()
+            if config.hoist == "all" and Fn.TargetInvariants.supported(net, src, tgt_c):
+                kw = {"invariants": Fn.TargetInvariants(net, tgt_c)}
+            else:
+                kw = {"tgt_tokens": net.emb_nn.forward_tokens(tgt_c)}
     for _ in range(iter):
-        if tgt_tok is not None:
-            srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt, tgt_tokens=tgt_tok)
-        else:
-            srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt)
+        srcK, src_corrK, R, t, _, _ = net(transformed_src, tgt, **kw)
         transformed_src = ops.rigid_apply(transformed_src, R, t)
         if R_f is None:
             R_f, t_f = R.detach().clone(), t.detach().clone()
@@ -247,12 +278,23 @@ class VCRNet(nn.Module):
             raise Exception("Not implemented")
         self.svd = SVDHead(args=args)
 
-    @torch.no_grad()      # registration INFERENCE path: only the LPD pre-training path (LPD / LPDNet) has a backward
-    def forward(self, *input, stages=None, tgt_tokens=None):
+    def forward(self, *input, stages=None, tgt_tokens=None, invariants=None):
+        # registration INFERENCE path: only the LPD pre-training path (LPD / LPDNet) has a backward
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "VCRNet training is not implemented on the B200 path (inference only: model/vcrnet_model.py:495-518 under "
+                "eval() / torch.no_grad(), as test_one_epoch runs it); LPD pre-training (--model=lpd) has a backward")
+        with torch.no_grad():
+            return self._forward(*input, stages=stages, tgt_tokens=tgt_tokens, invariants=invariants)
+
+    def _forward(self, *input, stages=None, tgt_tokens=None, invariants=None):
         src, tgt = input[0].contiguous(), input[1].contiguous()
         B = src.shape[0]
         same = src.shape == tgt.shape
-        if tgt_tokens is not None:                         # loop-invariant target embedding supplied by vcrnetIter
+        if invariants is not None:                         # loop-invariant target-side state supplied by vcrnetIter
+            Fn.emb_tokens(self.emb_nn, src, out=invariants.emb2[:B])
+            src_tok, tgt_tok = invariants.emb2[:B], invariants.emb2[B:]
+        elif tgt_tokens is not None:                       # loop-invariant target embedding supplied by vcrnetIter
             src_tok, tgt_tok = self.emb_nn.forward_tokens(src), tgt_tokens
         elif same:                                         # both clouds through ONE batch of 2B
             emb = self.emb_nn.forward_tokens(torch.cat([src, tgt], dim=0))
@@ -262,7 +304,15 @@ class VCRNet(nn.Module):
         if stages is not None:
             stages.update(src_emb0=src_tok, tgt_emb0=tgt_tok)
         pre = None
-        if isinstance(self.pointer, Transformer):
+        if isinstance(self.pointer, Identity):
+            # :502-505 with Identity: emb_p = emb, so emb + emb_p = 2 * emb for both clouds (head logits scale by 4)
+            src_tok, tgt_tok = src_tok * 2.0, tgt_tok * 2.0
+        elif isinstance(self.pointer, Transformer) and invariants is not None:
+            want_head = isinstance(self.head, VcpTopK)
+            res = Fn.transformer_tokens_hoisted(self.pointer, invariants, want_head=want_head)
+            src_tok, tgt_tok = res[0], res[1]
+            pre = res[2] if want_head else None
+        elif isinstance(self.pointer, Transformer):
             if isinstance(self.head, VcpTopK):     # the final LayerNorm also writes what the head derives from its output
                 src_tok, tgt_tok, pre = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True, want_head=True)
             else:
