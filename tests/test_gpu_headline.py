@@ -125,10 +125,10 @@ def _stats(x):
 
 
 # bars: set from the achieved numbers of the committed run (profiles/r02_parity_headline_*.json), with ~2x slack
-CFG1_R_MAX, CFG1_T_MAX = 2e-3, 2e-3            # worst pair (a flipped near-tie neighbour / a re-ordered key)
+CFG1_R_MAX, CFG1_T_MAX = 1.5e-3, 1.5e-3            # worst pair (a flipped near-tie neighbour / a re-ordered key)
 CFG1_R_MEDIAN = 1e-4                            # north_star's bar holds for the typical pair
-CFG1_METRIC_REL = 2e-3
-CFG2_METRIC_REL = 5e-2
+CFG1_METRIC_REL = 5e-4                          # achieved <= 1.2e-4 (the fp32 and fp64 reference differ by 2.3e-4)
+CFG2_METRIC_REL = 2e-2                          # achieved <= 7.4e-3 (the fp32 and fp64 reference differ by 7.3e-3)
 YARDSTICK = 4.0                                 # ours-vs-fp64 <= YARDSTICK * (fp32 reference vs fp64), on median and p90
 
 
@@ -195,11 +195,17 @@ def test_cfg2_partial_batch24_iter3_vs_live_reference(ckpt, precision, capsys, p
     with capsys.disabled():
         _report(f"cfg2_{precision}", rec)
     assert tuple(first[0].shape) == g["srcK"].shape
-    assert min(jac) >= 0.90 and np.median(jac) >= 0.97, (min(jac), np.median(jac))
-    assert min(agree) >= 0.98, min(agree)
-    assert np.median(eR) < 1e-3 and np.median(et) < 1e-3, (np.median(eR), np.median(et))
-    for q in (0.5, 0.9):
-        assert np.quantile(eR64, q) <= YARDSTICK * np.quantile(rR64, q) + 1e-5, (q, np.quantile(eR64, q), np.quantile(rR64, q))
-        assert np.quantile(et64, q) <= YARDSTICK * np.quantile(rt64, q) + 1e-5, (q, np.quantile(et64, q), np.quantile(rt64, q))
+    # iteration 1 (no chaos amplified yet): same selected sets, same hard correspondences, same pose
+    assert min(jac) >= 0.98 and np.median(jac) >= 0.99, (min(jac), np.median(jac))
+    assert min(agree) >= 0.99, min(agree)
+    assert np.mean(e1R < 1e-4) >= 0.9, np.mean(e1R < 1e-4)
+    # after 3 iterations the per-pair error is BIMODAL (a pair either keeps every hard selection, error ~1e-6, or flips
+    # one and lands ~1e-2 away): the fp32 reference itself agrees with its fp64 run on only 2/3 of these 48 pairs.  Bars:
+    # the share of agreeing pairs is within 0.25 of the reference's own, the tail is within YARDSTICK of the reference's.
+    ref_share = np.mean(rR64 < 1e-4)
+    assert np.mean(eR64 < 1e-4) >= ref_share - 0.25 and np.mean(eR < 1e-4) >= ref_share - 0.25, (np.mean(eR64 < 1e-4), ref_share)
+    assert np.quantile(eR64, 0.9) <= YARDSTICK * np.quantile(rR64, 0.9) + 1e-5, (np.quantile(eR64, 0.9), np.quantile(rR64, 0.9))
+    assert np.quantile(et64, 0.9) <= YARDSTICK * np.quantile(rt64, 0.9) + 1e-5, (np.quantile(et64, 0.9), np.quantile(rt64, 0.9))
+    assert eR64.max() <= YARDSTICK * rR64.max() and et64.max() <= YARDSTICK * rt64.max(), (eR64.max(), rR64.max())
     bad = {k: v for k, v in merr.items() if v > CFG2_METRIC_REL}
     assert not bad, bad

@@ -200,3 +200,20 @@ def test_dataparallel_replica_code_paths():
     assert "_vcr_packed_replica" not in net.__dict__
     rep2 = _cpu_replicate(net)                                                  # the next forward's replica starts clean
     assert "_vcr_packed_replica" not in rep2.__dict__
+
+
+def test_product_synthetic_helpers_match_the_test_infrastructure():
+    """bench.py builds its arguments, checkpoint and inputs from vcr_net_b200.synthetic (product side); they are the same
+    bytes oracle/synth (test infrastructure, the thing the golden vectors were generated with) produces."""
+    import numpy as np
+    from vcr_net_b200 import synthetic
+    from oracle import synth
+    from oracle.ref_harness import default_args
+    lpd = dict(np.load(os.path.join(ROOT, "tests", "golden", "lpd_pretrained_weights.npz")))
+    a, b = synthetic.state_dict(1234, emb_weights=lpd), synth.make_checkpoint(1234, emb_weights=lpd)
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert np.array_equal(a[k].numpy(), b[k]), k
+    assert vars(synthetic.default_args(partial=True, overlap2=0.7)) == vars(default_args(partial=True, overlap2=0.7))
+    r, o2 = synthetic.reserve_overlap2(0.575)
+    assert abs(r - synth.RESERVE_0575) < 1e-8 and abs(o2 - synth.OVERLAP2_0575) < 1e-8
