@@ -51,6 +51,11 @@ int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, in
 /* D == 3 route of vcr_knn_topk: 1 (default) = distances evaluated on the fly from x|y|z|xx rows in shared memory
  * (4 CTAs per SM), 0 = the generic distance-tile kernel.  Bit-identical indices; returns the previous setting. */
 int vcr_set_knn3_direct(int on);
+/* Selection of the tensor-core route (vcr_knn_topk_tc): 0 = warp-per-query from a shared-memory distance tile, 1 =
+ * thread-per-query straight from TMEM (queries on the M side of the MMA, register sorting networks; csrc/knn_tpq.cuh),
+ * 2 (default) = thread-per-query from N >= 8192, where it measured faster.  Bit-identical indices; returns the
+ * previous setting. */
+int vcr_set_knn_tc_tpq(int on);
 
 /* Tensor-core variant of the same function for feature-space kNN (16 <= D <= 128, k <= 30, token-major only):
  * tcgen05 distance tiles from the operand-format copy of x ([2 planes][B*N][ld] fp16 hi / lo*2^11, vcr_to_operand)

@@ -85,9 +85,19 @@ def test_knn_shapes(D, N, k, tm):
     assert np.array_equal(got, want)
 
 
+@pytest.fixture(params=[0, 1], ids=["warp-per-query", "thread-per-query"])
+def knn_tc_selection(request):
+    """Both selections of the tensor-core kNN route (csrc/knn.cu knn_tc_kernel, csrc/knn_tpq.cuh knn_tc2_kernel); the
+    default routes by N (thread-per-query from N >= 8192), so each is forced here."""
+    from vcr_net_b200._lib import lib
+    old = lib().vcr_set_knn_tc_tpq(request.param)
+    yield request.param
+    lib().vcr_set_knn_tc_tpq(old)
+
+
 @pytest.mark.parametrize("D,N,k", [(64, 130, 20), (64, 1024, 20), (64, 768, 20), (64, 2048, 20), (128, 515, 20),
                                    (16, 300, 5), (96, 257, 30), (32, 21, 20), (64, 4096, 20), (128, 1000, 1)])
-def test_knn_tc_prefilter_bit_exact(D, N, k):
+def test_knn_tc_prefilter_bit_exact(D, N, k, knn_tc_selection):
     """tcgen05 prefilter + exact re-rank == canonical C oracle, bit for bit; on generic data almost nothing needs the
     exact kernel."""
     rs = np.random.RandomState(N + D + k)
@@ -101,7 +111,7 @@ def test_knn_tc_prefilter_bit_exact(D, N, k):
     assert np.array_equal(nump(got64), want) and got64.dtype == torch.int64 and torch.equal(got32.long(), got64)
 
 
-def test_knn_tc_prefilter_adversarial_inputs():
+def test_knn_tc_prefilter_adversarial_inputs(knn_tc_selection):
     """Inputs that defeat the certificate (exact ties, duplicates, cancellation, out-of-range magnitudes) fall back to the
     exact kernel inside the same call: still bit-exact."""
     rs = np.random.RandomState(17)

@@ -793,6 +793,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
 }
 
+#include "knn_tpq.cuh"      // thread-per-query selection: knn3_tpq_kernel (D = 3, exact), knn_tc2_kernel (tcgen05 prefilter)
+
 }  // namespace
 
 VCR_API size_t vcr_knn_workspace_bytes(int B, int N) { return (size_t)B * N * sizeof(float); }
@@ -801,10 +803,18 @@ VCR_API size_t vcr_knn_workspace_bytes(int B, int N) { return (size_t)B * N * si
 // Either idx32 or idx64 (or both) may be given.  Requires 1 <= k <= 31, N >= k+1; any D >= 1 (D <= 4 is staged
 // 4 dims at a time, wider features 16 dims at a time).
 static std::atomic<int> g_vcr_knn3_direct{1};      // tuning knob (see vcr_set_knn3_direct)
+static std::atomic<int> g_vcr_knn_tc_tpq{2};       // tuning knob (see vcr_set_knn_tc_tpq)
 
 // D == 3: distances on the fly (knn3_kernel, default) or the generic tile kernel.  Same indices; returns the previous setting.
 VCR_API int vcr_set_knn3_direct(int on) {
     return g_vcr_knn3_direct.exchange(on ? 1 : 0);
+}
+
+// Feature-space tensor-core route: 1 = always the thread-per-query selection from TMEM (knn_tc2_kernel), 0 = always the
+// warp-per-query selection from a shared-memory distance tile (knn_tc_kernel), 2 (default) = thread-per-query from
+// N >= 8192, where it measured faster.  Same indices; returns the previous setting.
+VCR_API int vcr_set_knn_tc_tpq(int on) {
+    return g_vcr_knn_tc_tpq.exchange(on < 0 ? 0 : (on > 2 ? 2 : on));
 }
 
 VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_major, int32_t* idx32,
@@ -818,7 +828,8 @@ VCR_API int vcr_knn_topk(const float* x, int B, int D, int N, int k, int token_m
     else knn_sqnorm_kernel<false><<<g, 256, 0, stream>>>(x, D, N, xx);
     VCR_CHECK_LAUNCH();
     if (k > 31) return VCR_ERR_UNSUPPORTED;
-    if (D == 3 && g_vcr_knn3_direct.load(std::memory_order_relaxed)) {
+    const int route3 = g_vcr_knn3_direct.load(std::memory_order_relaxed);
+    if (D == 3 && route3 != 0) {
         dim3 grid(vcr_cdiv(N, TQ3), B);
         if (token_major) knn3_kernel<true><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);
         else knn3_kernel<false><<<grid, NT, 0, stream>>>(x, xx, N, k, idx32, idx64);
@@ -858,6 +869,23 @@ VCR_API int vcr_knn_topk_tc(const float* x, const void* xop, int ld, long long p
     knn_sqnorm_max_kernel<<<g, 256, 0, stream>>>(x, D, N, xx, xxmax);
     VCR_CHECK_LAUNCH();
     CUtensorMap tmC, tmQ;
+    const int tpq = g_vcr_knn_tc_tpq.load(std::memory_order_relaxed);
+    if (tpq == 1 || (tpq == 2 && N >= 8192)) {
+        int rc = vcr_make_operand_tmap(&tmC, xop, D, (long long)B * N, ld, plane_stride, 2, TC2);
+        if (rc != VCR_OK) return rc;
+        rc = vcr_make_operand_tmap(&tmQ, xop, D, (long long)B * N, ld, plane_stride, 2, TQ2);
+        if (rc != VCR_OK) return rc;
+        KnnTcParams p;
+        p.x = x; p.xx = xx; p.xxmax = xxmax; p.redo = redo; p.nflag = nflag;
+        p.D = D; p.N = N; p.k = k; p.ksel = k + 8 < 31 ? k + 8 : 31; p.KB = (D + 63) / 64;
+        p.idx32 = idx32; p.idx64 = idx64;
+        const size_t smem = knn_tc2_smem_bytes(p.KB);
+        if (cudaFuncSetAttribute(knn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return VCR_ERR_LAUNCH;
+        knn_tc2_kernel<<<dim3(vcr_cdiv(N, TQ2), B), T2_THREADS, smem, stream>>>(tmC, tmQ, p);
+        VCR_CHECK_LAUNCH();
+        return launch_knn<16, true>(x, xx, B, D, N, k, idx32, idx64, stream, redo);   // repairs flagged groups only
+    }
     int rc = vcr_make_operand_tmap(&tmC, xop, D, (long long)B * N, ld, plane_stride, 2, T2M);
     if (rc != VCR_OK) return rc;
     rc = vcr_make_operand_tmap(&tmQ, xop, D, (long long)B * N, ld, plane_stride, 2, TQ);
