@@ -504,7 +504,7 @@ def rooflines_from_profile(prof, nprof, precision, peaks, protos):
                 r["fp32_tflops"] = d["flops"] / (d["ms"] / 1e3) / 1e12
         else:
             continue
-        ev = ncu_evidence(entry)
+        ev = ncu_evidence(key) or (ncu_evidence(entry) if key == entry else None)
         r["traffic"] = ev["mean_dram_bytes_per_launch"] if ev else None
         if ev:
             r["ncu"] = ev
