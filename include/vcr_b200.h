@@ -215,6 +215,17 @@ int vcr_softcorr_best_tc(const void* S, int lds, long long s_plane, const void* 
 size_t vcr_rowsum_colsoftmax_workspace_bytes(int B, int Nt);
 int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt, float* out, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
+/* selectCom (model/vcrnet_model.py:213-222, 243-244) selection statistics in two reads of the score products:
+ * pd_ij = (-xx_i - (-2 dot_ij)) - yy_j is formed on the fly (dot [B,Ns,ld] is left untouched); row_stat [B,Ns] = row sums of
+ * the column softmax, col_stat [B,Nt] = column sums of the row softmax.  Deterministic (fixed slab order). */
+size_t vcr_select_stats_workspace_bytes(int B, int Ns, int Nt);
+int vcr_select_stats(const float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
+                     float* row_stat, float* col_stat, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Rows idx[b,:] of an operand-format buffer ([2 planes][B*Nin][ld_in], 16-bit) and of its squared row norms: what getCopair
+ * (model/vcrnet_model.py:264-332) needs of the points selectCom kept, without going back through fp32. */
+int vcr_gather_operand_rows(const void* in, int ld_in, long long plane_in, int B, int Nin, const int* idx, int K,
+                            int C, void* out, int ld_out, long long plane_out, const float* sq_in, float* sq_out,
+                            cudaStream_t stream);
 int vcr_gather_rows(const float* in, int ld_in, int B, int Nin, const int* idx, int K, int C, float* out,
                     int ld_out, cudaStream_t stream);
 int vcr_gather_cols(const float* in, int B, int C, int Nin, const int* idx, int K, float* out, cudaStream_t stream);

@@ -586,6 +586,46 @@ def test_vcrnet_training_mode_raises_clearly(net_whole):
     finally:
         net_whole.eval()
 
+
+@pytest.mark.parametrize("B,Ns,Nt", [(2, 768, 768), (3, 257, 331), (1, 40, 1024), (2, 100, 64)])
+def test_select_stats_fused_two_read_pass(B, Ns, Nt):
+    """vcr_select_stats: selectCom's two statistics (model/vcrnet_model.py:213-222, 243-244) straight from the score
+    products, pd formed on the fly -- against fp64 numpy, incl. ragged sizes (element-wise load path) and the old
+    negdist -> column-softmax / row-softmax kernels."""
+    rs = np.random.RandomState(Ns + Nt)
+    s = (rs.randn(B, Ns, 32) * 0.7).astype(np.float32)
+    t = (rs.randn(B, Nt, 32) * 0.7).astype(np.float32)
+    st, tt = cu(s), cu(t)
+    dot, ld = ops.pair_dots(st, tt)
+    xx, yy = ops.sqnorm_rows(st), ops.sqnorm_rows(tt)
+    row_stat, col_stat = ops.select_stats(dot, ld, Ns, Nt, xx, yy)
+    d64 = nump(dot)[:, :, :Nt].astype(np.float64)
+    pd = (-nump(xx).astype(np.float64)[:, :, None] + 2.0 * d64) - nump(yy).astype(np.float64)[:, None, :]
+    e_r = np.exp(pd - pd.max(axis=2, keepdims=True)); p_r = e_r / e_r.sum(axis=2, keepdims=True)
+    e_c = np.exp(pd - pd.max(axis=1, keepdims=True)); p_c = e_c / e_c.sum(axis=1, keepdims=True)
+    assert rel_err(nump(col_stat), p_r.sum(axis=1)) < 2e-5
+    assert rel_err(nump(row_stat), p_c.sum(axis=2)) < 2e-5
+    # the materialised path of round 1 (kept for the reference-named API) agrees
+    pdm = ops.negdist_(dot.clone(), ld, Ns, Nt, xx, yy)
+    old_row = ops.rowsum_colsoftmax(pdm, ld, Ns, Nt)
+    P = ops.softmax_rows_(pdm.view(B * Ns, ld)[:, :Nt])
+    old_col = ops.colsum(P, B)
+    assert rel_err(nump(row_stat), nump(old_row)) < 2e-5 and rel_err(nump(col_stat), nump(old_col)) < 2e-5
+
+
+def test_gather_operand_rows_matches_fp32_gather():
+    """getCopair's inputs gathered in operand format: same bits as gather_rows + to_operand + sqnorm_rows of the fp32 rows."""
+    rs = np.random.RandomState(5)
+    B, N, D, K = 3, 200, 512, 77
+    x = cu(rs.randn(B, N, D).astype(np.float32))
+    idx = cu(np.stack([rs.permutation(N)[:K] for _ in range(B)]).astype(np.int32))
+    op = ops.to_operand(x.view(B * N, D), "h3")
+    sq = ops.sqnorm_rows(x)
+    g_op, g_sq = ops.gather_operand_rows(op, sq, idx, B, N)
+    rows = ops.gather_rows(x, idx)
+    want = ops.to_operand(rows.view(B * K, D), "h3")
+    assert torch.equal(g_op.buf, want.buf) and torch.equal(g_sq, ops.sqnorm_rows(rows))
+
 # ---------------------------------------------------------------- tensor-core GEMM --------------------
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 520, 200), (4096, 1536, 512), (300, 64, 1024)])
 def test_gemm_tc_h3_matches_fp64(M, N, K):

@@ -94,7 +94,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
             const float4 e = rr[lane + i * 32];
             r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
         }
-        o[lane + i * 32] = r;
+        if (!EXTRA || out != nullptr) o[lane + i * 32] = r;      // EXTRA: the fp32 copy is optional (the head reads op / sq)
         if (EXTRA) v[i] = r;
     }
     if (EXTRA) {
@@ -491,6 +491,154 @@ __global__ void negdist_kernel(float* __restrict__ dot, int ld, int Ns, int Nt, 
     r[j] = __fsub_rn(__fsub_rn(-xx[(size_t)b * Ns + i], -2.f * r[j]), yy[(size_t)b * Nt + j]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// selectCom statistics in two reads of the score products (model/vcrnet_model.py:213-222, 243-244):
+//   pd_ij    = (-xx_i - (-2 dot_ij)) - yy_j                              (reference op order, never written back)
+//   col_stat = sum_i softmax_j(pd)_ij   (row softmax, summed over rows)    -> picks the target points (:222)
+//   row_stat = sum_j softmax_i(pd)_ij   (column softmax, summed over cols) -> picks the source points (:244)
+// A CTA owns a slab of RS rows of one pair, staged as pd in shared memory.  Pass A: exact row (max, sum exp) per row and
+// per-slab column (max, sum exp) partials; a small kernel combines the slabs per column in slab order; pass B recomputes
+// pd and accumulates both weighted sums (rows complete, columns as per-slab partials reduced in slab order by
+// colsum_final_kernel).  Replaces negdist (R+W) + col_max / col_sum partials + rowsum_colsoftmax + softmax_rows (3R+2W) +
+// colsum: ~9 reads and 3 writes of the [Ns, Nt] matrix become 2 reads.  Deterministic (fixed slab order, no atomics).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_T = 256;
+constexpr int SEL_RS = SEL_T / 32;          // rows per slab: one warp per row
+
+// warp `warp` loads row i0 + warp of the slab: pd values into shared memory (for the column phase) and, lane-strided by
+// float4, into v[] (for the row phase) -- no second pass over shared memory for the rows.  Columns past Nt hold -inf.
+template <int NV>
+__device__ __forceinline__ void sel_load_row(const float* __restrict__ drow, int Nt, float nx, const float* __restrict__ yy,
+                                             float* srow, float4 (&v)[NV], int lane, int vec) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = (lane + q * 32) * 4;
+        float4 o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (vec) {
+            if (c < Nt) {
+                const float4 d = *reinterpret_cast<const float4*>(drow + c);
+                const float4 y = *reinterpret_cast<const float4*>(yy + c);
+                o.x = __fsub_rn(__fsub_rn(nx, -2.f * d.x), y.x); o.y = __fsub_rn(__fsub_rn(nx, -2.f * d.y), y.y);
+                o.z = __fsub_rn(__fsub_rn(nx, -2.f * d.z), y.z); o.w = __fsub_rn(__fsub_rn(nx, -2.f * d.w), y.w);
+            }
+        } else {                                          // ragged / unaligned: element-wise
+            if (c + 0 < Nt) o.x = __fsub_rn(__fsub_rn(nx, -2.f * drow[c + 0]), yy[c + 0]);
+            if (c + 1 < Nt) o.y = __fsub_rn(__fsub_rn(nx, -2.f * drow[c + 1]), yy[c + 1]);
+            if (c + 2 < Nt) o.z = __fsub_rn(__fsub_rn(nx, -2.f * drow[c + 2]), yy[c + 2]);
+            if (c + 3 < Nt) o.w = __fsub_rn(__fsub_rn(nx, -2.f * drow[c + 3]), yy[c + 3]);
+        }
+        v[q] = o;
+        *reinterpret_cast<float4*>(srow + c) = o;         // ldp >= 128 * NV: always in range
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(SEL_T)
+select_stats_a_kernel(const float* __restrict__ dot, int ld, int Ns, int Nt, int vec, const float* __restrict__ xx,
+                      const float* __restrict__ yy, float* __restrict__ rmax, float* __restrict__ rsum,
+                      float* __restrict__ pmax, float* __restrict__ psum) {
+    constexpr int LDP = NV * 128;
+    __shared__ __align__(16) float sm[SEL_RS * LDP];
+    const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
+    const int i0 = slab * SEL_RS, nr = min(SEL_RS, Ns - i0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < nr) {
+        const int i = i0 + warp;
+        float4 v[NV];
+        sel_load_row<NV>(dot + ((size_t)b * Ns + i) * ld, Nt, -xx[(size_t)b * Ns + i], yy + (size_t)b * Nt, sm + warp * LDP, v,
+                         lane, vec);
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) m = fmaxf(fmaxf(m, fmaxf(v[q].x, v[q].y)), fmaxf(v[q].z, v[q].w));
+        m = warp_max(m);
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sacc += (expf(v[q].x - m) + expf(v[q].y - m)) + (expf(v[q].z - m) + expf(v[q].w - m));
+        sacc = warp_sum(sacc);                            // padded columns are -inf: exp gives exactly 0
+        if (lane == 0) { rmax[(size_t)b * Ns + i] = m; rsum[(size_t)b * Ns + i] = sacc; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < Nt; j += SEL_T) {
+        float m = -INFINITY;
+        for (int r = 0; r < nr; ++r) m = fmaxf(m, sm[r * LDP + j]);
+        float sacc = 0.f;
+        for (int r = 0; r < nr; ++r) sacc += expf(sm[r * LDP + j] - m);
+        pmax[((size_t)b * slabs + slab) * Nt + j] = m;
+        psum[((size_t)b * slabs + slab) * Nt + j] = sacc;
+    }
+}
+__global__ void select_stats_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int slabs, int Nt,
+                                            float* __restrict__ cmax, float* __restrict__ csum) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= Nt) return;
+    float m = -INFINITY;
+    for (int t = 0; t < slabs; ++t) m = fmaxf(m, pmax[((size_t)b * slabs + t) * Nt + j]);
+    float sacc = 0.f;
+    for (int t = 0; t < slabs; ++t) sacc += psum[((size_t)b * slabs + t) * Nt + j] * expf(pmax[((size_t)b * slabs + t) * Nt + j] - m);
+    cmax[(size_t)b * Nt + j] = m;
+    csum[(size_t)b * Nt + j] = sacc;
+}
+template <int NV>
+__global__ void __launch_bounds__(SEL_T)
+select_stats_b_kernel(const float* __restrict__ dot, int ld, int Ns, int Nt, int vec, const float* __restrict__ xx,
+                      const float* __restrict__ yy, const float* __restrict__ rmax, const float* __restrict__ rsum,
+                      const float* __restrict__ cmax, const float* __restrict__ csum, float* __restrict__ row_stat,
+                      float* __restrict__ cpart) {
+    constexpr int LDP = NV * 128;
+    __shared__ __align__(16) float sm[SEL_RS * LDP];
+    __shared__ float s_rm[SEL_RS], s_rs[SEL_RS];
+    const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
+    const int i0 = slab * SEL_RS, nr = min(SEL_RS, Ns - i0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* cm = cmax + (size_t)b * Nt;
+    const float* cs = csum + (size_t)b * Nt;
+    if (warp < nr) {                                       // column softmax, summed along the row (:243-244)
+        const int i = i0 + warp;
+        float4 v[NV];
+        sel_load_row<NV>(dot + ((size_t)b * Ns + i) * ld, Nt, -xx[(size_t)b * Ns + i], yy + (size_t)b * Nt, sm + warp * LDP, v,
+                         lane, vec);
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int c = (lane + q * 32) * 4;
+            const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c + u < Nt) sacc += expf(e[u] - cm[c + u]) / cs[c + u];
+        }
+        sacc = warp_sum(sacc);
+        if (lane == 0) {
+            row_stat[(size_t)b * Ns + i] = sacc;
+            s_rm[warp] = rmax[(size_t)b * Ns + i]; s_rs[warp] = rsum[(size_t)b * Ns + i];
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < Nt; j += SEL_T) {        // row softmax, summed down the column (:221-222)
+        float sacc = 0.f;
+        for (int r = 0; r < nr; ++r) sacc += expf(sm[r * LDP + j] - s_rm[r]) / s_rs[r];
+        cpart[((size_t)b * slabs + slab) * Nt + j] = sacc;
+    }
+}
+
+// operand-format row gather: out[pl][b*K + r][:] = in[pl][b*Nin + idx[b, r]][:] for both planes, sq_out[b, r] = sq_in[b, idx[b, r]]
+// (the rows and squared norms getCopair needs of the points selectCom kept; C % 8 == 0).  One warp per output row.
+__global__ void gather_operand_rows_kernel(const __half* __restrict__ in, int ld_in, long long plane_in, int Nin,
+                                           const int* __restrict__ idx, int K, int C, __half* __restrict__ out, int ld_out,
+                                           long long plane_out, const float* __restrict__ sq_in, float* __restrict__ sq_out) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= K) return;
+    const int src = idx[(size_t)b * K + r];
+    const __half* ip = in + ((size_t)b * Nin + src) * ld_in;
+    __half* op = out + ((size_t)b * K + r) * ld_out;
+    for (int c = lane * 8; c < C; c += 256) {
+        *reinterpret_cast<uint4*>(op + c) = *reinterpret_cast<const uint4*>(ip + c);
+        *reinterpret_cast<uint4*>(op + plane_out + c) = *reinterpret_cast<const uint4*>(ip + plane_in + c);
+    }
+    if (lane == 0 && sq_in) sq_out[(size_t)b * K + r] = sq_in[(size_t)b * Nin + src];
+}
+
 // gather rows: out[b, r, :] = in[b, idx[b, r], :]   (C % 4 == 0)
 __global__ void gather_rows_kernel(const float* __restrict__ in, int ld_in, int Nin, const int* __restrict__ idx,
                                    int K, int C, float* __restrict__ out, int ld_out) {
@@ -580,8 +728,8 @@ VCR_API int vcr_layernorm(const float* x, int ldx, const float* a, const float* 
 VCR_API int vcr_layernorm_head(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
                                const float* residual, int ldr, float* out, int ldo, void* op, int ldop,
                                long long plane_stride, float* sq, cudaStream_t stream) {
-    VCR_REQUIRE(x && a && b && out && op && sq && M > 0);
-    if (D % 128 != 0 || D > 1024 || (ldx & 3) || (ldo & 3) || (residual && (ldr & 3)) || (ldop & 3) || (plane_stride & 3))
+    VCR_REQUIRE(x && a && b && op && sq && M > 0);             // out may be NULL: operand copy + norms only
+    if (D % 128 != 0 || D > 1024 || (ldx & 3) || (out && (ldo & 3)) || (residual && (ldr & 3)) || (ldop & 3) || (plane_stride & 3))
         return VCR_ERR_UNSUPPORTED;
     const int wpb = 8;
     dim3 g(vcr_cdiv(M, wpb));
@@ -765,6 +913,63 @@ VCR_API int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt
     VCR_CHECK_LAUNCH();
     dim3 g2(vcr_cdiv(Ns, 8), B);
     rowsum_colsoftmax_kernel<<<g2, 256, 0, stream>>>(pd, ld, Ns, Nt, cmax, csum, out);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+VCR_API size_t vcr_select_stats_workspace_bytes(int B, int Ns, int Nt) {
+    const size_t slabs = (size_t)(Ns + SEL_RS - 1) / SEL_RS;
+    return ((size_t)2 * B * Ns + (size_t)2 * B * Nt + (size_t)3 * B * slabs * Nt) * sizeof(float);
+}
+// selectCom's two selection statistics from the score products dot[B, Ns, ld] (left untouched), xx [B, Ns], yy [B, Nt]:
+// row_stat [B, Ns] = row sums of the column softmax of pd, col_stat [B, Nt] = column sums of the row softmax of pd.
+// Nt <= 1024 (a warp holds a row in registers).
+VCR_API int vcr_select_stats(const float* dot, int ld, int B, int Ns, int Nt, const float* xx, const float* yy,
+                             float* row_stat, float* col_stat, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream) {
+    VCR_REQUIRE(dot && xx && yy && row_stat && col_stat && B > 0 && Ns > 0 && Nt > 0 && B <= 65535);
+    if (Nt > 1024) return VCR_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vcr_select_stats_workspace_bytes(B, Ns, Nt)) return VCR_ERR_WORKSPACE;
+    // float4 loads of the dot rows and of yy[b, :] when everything is 16-byte aligned, element-wise otherwise
+    const int vec = (Nt & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dot) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(yy) & 15) == 0;
+    const int slabs = (Ns + SEL_RS - 1) / SEL_RS;
+    float* rmax = reinterpret_cast<float*>(workspace);
+    float* rsum = rmax + (size_t)B * Ns;
+    float* cmax = rsum + (size_t)B * Ns;
+    float* csum = cmax + (size_t)B * Nt;
+    float* pmax = csum + (size_t)B * Nt;
+    float* psum = pmax + (size_t)B * slabs * Nt;
+    float* cpart = psum + (size_t)B * slabs * Nt;
+    dim3 g(slabs, B), gc(vcr_cdiv(Nt, 128), B);
+    switch ((Nt + 127) / 128) {
+#define SEL_CASE(V) case V: select_stats_a_kernel<V><<<g, SEL_T, 0, stream>>>(dot, ld, Ns, Nt, vec, xx, yy, rmax, rsum, pmax, psum); break;
+        SEL_CASE(1) SEL_CASE(2) SEL_CASE(3) SEL_CASE(4) SEL_CASE(5) SEL_CASE(6) SEL_CASE(7) SEL_CASE(8)
+#undef SEL_CASE
+    }
+    VCR_CHECK_LAUNCH();
+    select_stats_combine_kernel<<<gc, 128, 0, stream>>>(pmax, psum, slabs, Nt, cmax, csum);
+    VCR_CHECK_LAUNCH();
+    switch ((Nt + 127) / 128) {
+#define SEL_CASE(V) case V: select_stats_b_kernel<V><<<g, SEL_T, 0, stream>>>(dot, ld, Ns, Nt, vec, xx, yy, rmax, rsum, cmax, csum, row_stat, cpart); break;
+        SEL_CASE(1) SEL_CASE(2) SEL_CASE(3) SEL_CASE(4) SEL_CASE(5) SEL_CASE(6) SEL_CASE(7) SEL_CASE(8)
+#undef SEL_CASE
+    }
+    VCR_CHECK_LAUNCH();
+    colsum_final_kernel<<<gc, 128, 0, stream>>>(cpart, slabs, Nt, col_stat);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
+// Rows idx[b, :] of an operand-format buffer ([2 planes][B*Nin][ld_in] 16-bit) and of its squared norms, per batch item.
+VCR_API int vcr_gather_operand_rows(const void* in, int ld_in, long long plane_in, int B, int Nin, const int* idx, int K,
+                                    int C, void* out, int ld_out, long long plane_out, const float* sq_in, float* sq_out,
+                                    cudaStream_t stream) {
+    VCR_REQUIRE(in && idx && out && B > 0 && K > 0 && C > 0 && B <= 65535 && (!sq_in || sq_out));
+    if ((C & 7) || (ld_in & 7) || (ld_out & 7) || (plane_in & 7) || (plane_out & 7)) return VCR_ERR_UNSUPPORTED;
+    dim3 g(vcr_cdiv(K, 8), B);
+    gather_operand_rows_kernel<<<g, 256, 0, stream>>>(reinterpret_cast<const __half*>(in), ld_in, plane_in, Nin, idx, K, C,
+                                                      reinterpret_cast<__half*>(out), ld_out, plane_out, sq_in, sq_out);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }

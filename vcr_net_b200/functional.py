@@ -637,7 +637,7 @@ class HeadPre:
         self.op, self.sq = op, sq
 
 
-def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False, want_head=False):
+def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False, want_head=False, want_out=True):
     """swap_mem: decoder batch item b attends to the encoder output of item (b + B/2) mod B -- the two directions of
     Transformer.forward run as one batch [src; tgt] without building the swapped copy [tgt; src]: only the encoder's
     final LayerNorm writes its two halves exchanged."""
@@ -661,7 +661,7 @@ def encoder_decoder_tc(model, src, tgt, final_residual, mode, swap_mem=False, wa
         y = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[2].norm, y, mode), B * Nt, y, mode)
     if want_head:
         nrm = model.decoder.norm
-        return ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=final_residual)
+        return ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=final_residual, want_out=want_out)
     return _ln(model.decoder.norm, y, residual=final_residual)
 
 
@@ -730,7 +730,7 @@ def emb_tokens(emb_nn, xyz, out=None):
     return out
 
 
-def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False):
+def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False, want_out=True):
     """One refinement iteration of Transformer.forward + the VCRNet residual (model/transformer.py:264-272,
     model/vcrnet_model.py:504-505) given the target-side invariants; ``inv.emb2[:B]`` holds this iteration's emb(src).
     Returns what transformer_tokens(add_input=True) returns."""
@@ -761,14 +761,14 @@ def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False):
         y = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[2].norm, y, mode), 2 * B * N, y, mode)
     nrm = model.decoder.norm
     if want_head:
-        out, op, sq = ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=inv.emb2)
+        out, op, sq = ops.layernorm_head(y, nrm.a_2, nrm.b_2, nrm.eps, residual=inv.emb2, want_out=want_out)
         pre = (HeadPre(op.rows_view(0, B * N), sq[:B]), HeadPre(op.rows_view(B * N, B * N), sq[B:]))
-        return out[:B], out[B:], pre
+        return (out[:B], out[B:], pre) if out is not None else (None, None, pre)
     out = _ln(nrm, y, residual=inv.emb2)
     return out[:B], out[B:]
 
 
-def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_input=False, want_head=False):
+def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_input=False, want_head=False, want_out=True):
     """Transformer.forward on tokens (model/transformer.py:264-272).  The two directions
     (model(src,tgt) -> tgt_p and model(tgt,src) -> src_p) share weights and are independent, so
     they run as ONE batch of 2B.  Returns (src_p, tgt_p) tokens; with ``add_input`` the
@@ -785,12 +785,12 @@ def transformer_tokens(tr, src_tok: torch.Tensor, tgt_tok: torch.Tensor, add_inp
         if config.precision != "fp32":
             enc_in = enc_in.contiguous()
             out = encoder_decoder_tc(tr.model, enc_in, enc_in, enc_in if add_input else None, config.precision, swap_mem=True,
-                                     want_head=want_head)
+                                     want_head=want_head, want_out=want_out)
             if want_head:
                 out, op, sq = out
-                n = out.shape[1]
+                n = enc_in.shape[1]
                 pre = (HeadPre(op.rows_view(0, B * n), sq[:B]), HeadPre(op.rows_view(B * n, B * n), sq[B:]))
-                return out[:B], out[B:], pre
+                return (out[:B], out[B:], pre) if out is not None else (None, None, pre)
             return out[:B], out[B:]
         dec_in = torch.cat([tgt_tok, src_tok], dim=0)
         out = encoder_decoder_tok(tr.model, enc_in, dec_in, final_residual=dec_in if add_input else None)
@@ -827,10 +827,13 @@ def pair_dots(src_tok, tgt_tok, alpha=1.0, pre=None):
 def vcp_whole(src_tok, tgt_tok, tgt_xyz, pre=None):
     """getCopairALL (model/vcrnet_model.py:334-347): src_corr [B,3,N].  pre: (HeadPre src, HeadPre tgt) from the final
     LayerNorm of the Transformer (operand copies + squared norms already in HBM)."""
-    B, Ns, D = src_tok.shape
-    Nt = tgt_tok.shape[1]
     if pre is not None and config.precision == "fp32":
         pre = None
+    if pre is not None:
+        B, Ns, Nt, D = pre[0].sq.shape[0], pre[0].sq.shape[1], pre[1].sq.shape[1], pre[0].op.cols
+    else:
+        B, Ns, D = src_tok.shape
+        Nt = tgt_tok.shape[1]
     xx, yy = (pre[0].sq, pre[1].sq) if pre is not None else (ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok))
     if config.precision != "fp32" and config.fused_softcorr:
         # one kernel: 3-term tcgen05 products + online softmax + weighted sum of the target points in the epilogue
@@ -862,40 +865,73 @@ def vcp_att(m, src_tok, tgt_tok, tgt_xyz):
     return vcp_whole(q, k, tgt_xyz)
 
 
-def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2, pre=None):
-    """selectCom (model/vcrnet_model.py:190-262) without the unused *_remain host round trips."""
-    B, Ns, D = src_tok.shape
-    Nt = tgt_tok.shape[1]
-    srcK = int(Ns * 0.84 * overlap2)
-    tgtK = int(Nt * 0.84 * overlap2)
-    src_tok, tgt_tok = src_tok.contiguous(), tgt_tok.contiguous()
+class Selected:
+    """selectCom's output on the tensor-core path: the kept points' embeddings as "h3" operand rows + squared norms
+    (gathered from the copies the Transformer's final LayerNorm wrote), never going back through fp32."""
+
+    def __init__(self, op, sq):
+        self.op, self.sq = op, sq
+
+
+def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2, pre=None, want_tokens=True):
+    """selectCom (model/vcrnet_model.py:190-262) without the unused *_remain host round trips.
+
+    The two selection statistics come from one fused two-read pass over the score products (vcr_select_stats).  With
+    ``pre`` (operand copies + squared norms of both embeddings) and ``want_tokens=False`` the selected embeddings are
+    returned as ``Selected`` operand rows for vcp_copair instead of fp32 tokens (src_tok / tgt_tok may then be None)."""
     if pre is not None and config.precision == "fp32":
         pre = None
-    dot, ld = pair_dots(src_tok, tgt_tok, pre=pre)
-    xx, yy = (pre[0].sq, pre[1].sq) if pre is not None else (ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok))
-    pd = ops.negdist_(dot, ld, Ns, Nt, xx, yy)                        # scores (:213-214)
-    row_stat = ops.rowsum_colsoftmax(pd, ld, Ns, Nt)                  # softmax over dim=1, sum dim=2 (:243-244)
-    P = ops.softmax_rows_(pd.view(B * Ns, ld)[:, :Nt])                # softmax over dim=2 (:221)
-    col_stat = ops.colsum(P, B)                                       # sum over dim=1 (:222)
+    ref = pre[0].sq if pre is not None else src_tok
+    B, Ns = ref.shape[0], ref.shape[1]
+    Nt = pre[1].sq.shape[1] if pre is not None else tgt_tok.shape[1]
+    srcK = int(Ns * 0.84 * overlap2)
+    tgtK = int(Nt * 0.84 * overlap2)
+    if pre is None:
+        src_tok, tgt_tok = src_tok.contiguous(), tgt_tok.contiguous()
+        dot, ld = pair_dots(src_tok, tgt_tok)
+        xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
+    else:
+        D = pre[0].op.cols
+        ld = (Nt + 3) // 4 * 4
+        dot = torch.empty((B, Ns, ld), dtype=_F32, device=pre[0].sq.device)
+        ops.gemm_tc(pre[0].op, pre[1].op, Ns, Nt, D, nbo=B, a_off=(Ns, 0, 0, 0), b_off=(Nt, 0, 0, 0), c=dot,
+                    c_strides=(Ns * ld, 0))
+        xx, yy = pre[0].sq, pre[1].sq
+    if Nt <= 1024:
+        # scores (:213-214), both softmaxes and their sums (:221-222, :243-244) in one fused two-read pass
+        row_stat, col_stat = ops.select_stats(dot, ld, Ns, Nt, xx, yy)
+    else:                                                              # materialised passes for long clouds
+        pd = ops.negdist_(dot, ld, Ns, Nt, xx, yy)
+        row_stat = ops.rowsum_colsoftmax(pd, ld, Ns, Nt)
+        col_stat = ops.colsum(ops.softmax_rows_(pd.view(B * Ns, ld)[:, :Nt]), B)
     idx_t, _ = ops.topk_select(col_stat, tgtK)
     idx_s, _ = ops.topk_select(row_stat, srcK)
-    return (ops.gather_cols(src_xyz, idx_s), ops.gather_rows(src_tok, idx_s),
-            ops.gather_cols(tgt_xyz, idx_t), ops.gather_rows(tgt_tok, idx_t), idx_s, idx_t)
+    so, to = ops.gather_cols(src_xyz, idx_s), ops.gather_cols(tgt_xyz, idx_t)
+    if pre is not None and not want_tokens:
+        s_sel = Selected(*ops.gather_operand_rows(pre[0].op, pre[0].sq, idx_s, B, Ns))
+        t_sel = Selected(*ops.gather_operand_rows(pre[1].op, pre[1].sq, idx_t, B, Nt))
+        return so, s_sel, to, t_sel, idx_s, idx_t
+    return so, ops.gather_rows(src_tok, idx_s), to, ops.gather_rows(tgt_tok, idx_t), idx_s, idx_t
 
 
 def vcp_copair(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2):
     """getCopair (model/vcrnet_model.py:264-332): hard arg-max correspondences for the
-    int(Ns*0.52*overlap2) most confident sources (tgtK == 1 makes val/val_sum == 1)."""
-    B, Ns, D = src_tok.shape
-    Nt = tgt_tok.shape[1]
+    int(Ns*0.52*overlap2) most confident sources (tgtK == 1 makes val/val_sum == 1).
+    src_tok / tgt_tok: fp32 tokens [B,N,D], or ``Selected`` operand rows from vcp_select."""
+    B, _, Ns = src_xyz.shape
+    Nt = tgt_xyz.shape[2]
     srcK = int(Ns * 0.52 * overlap2)
-    xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
-    if config.precision != "fp32" and config.fused_softcorr:
-        best_i, best_v = ops.softcorr_best_tc(ops.to_operand(src_tok.reshape(B * Ns, D), "h3"),
-                                              ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3"), xx, yy, B, Ns, Nt, D)
+    if isinstance(src_tok, Selected):
+        best_i, best_v = ops.softcorr_best_tc(src_tok.op, tgt_tok.op, src_tok.sq, tgt_tok.sq, B, Ns, Nt, src_tok.op.cols)
     else:
-        dot, ld = pair_dots(src_tok, tgt_tok)
-        _, best_i, best_v = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
+        D = src_tok.shape[2]
+        xx, yy = ops.sqnorm_rows(src_tok), ops.sqnorm_rows(tgt_tok)
+        if config.precision != "fp32" and config.fused_softcorr:
+            best_i, best_v = ops.softcorr_best_tc(ops.to_operand(src_tok.reshape(B * Ns, D), "h3"),
+                                                  ops.to_operand(tgt_tok.reshape(B * Nt, D), "h3"), xx, yy, B, Ns, Nt, D)
+        else:
+            dot, ld = pair_dots(src_tok, tgt_tok)
+            _, best_i, best_v = ops.softcorr_rows(dot, ld, Ns, Nt, xx, yy, mode=2)
     keep, _ = ops.topk_select(best_v, srcK)                            # [B,srcK] sorted by confidence
     src_k, corr_k = ops.copair_gather(src_xyz, tgt_xyz, keep, best_i)
     return src_k, corr_k, keep, best_i

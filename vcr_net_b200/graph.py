@@ -25,7 +25,9 @@ class GraphedRegistration:
                  device=None, warmup: int = 2):
         if not torch.cuda.is_available():
             raise RuntimeError("vcr_net_b200.graph needs a CUDA device (no CPU fallback exists)")
-        self.net, self.iter = net, int(iter)
+        # no strong reference to the network: vcrnetIter keeps these objects in a cache ON the network, and a cycle
+        # would leave dropped networks (and their graphs' memory pools) to the cyclic collector instead of refcounting
+        self.iter = int(iter)
         dev = torch.device(device) if device is not None else next(net.parameters()).device
         nt = num_points if num_points_tgt is None else num_points_tgt
         self.src = torch.zeros((batch, 3, num_points), dtype=torch.float32, device=dev)
@@ -44,8 +46,19 @@ class GraphedRegistration:
         torch.cuda.synchronize(dev)
         from ._lib import lib
         n0 = lib().vcr_launch_count()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self.out = vcrnetIter(net, self.src, self.tgt, iter=self.iter)
+        # Python's cyclic GC must not run inside the capture: collecting an unreachable older CUDAGraph there calls
+        # cudaGraphExecDestroy / cudaFree on the capturing thread, which invalidates a global-mode capture (seen as a
+        # launch failure of whichever kernel comes next).  Collect first, then hold the collector off until the capture ends.
+        import gc
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.out = vcrnetIter(net, self.src, self.tgt, iter=self.iter)
+        finally:
+            if gc_was_on:
+                gc.enable()
         self.launches_per_replay = int(lib().vcr_launch_count() - n0)      # kernels of this library inside the graph
 
     def __call__(self, src: torch.Tensor, tgt: torch.Tensor):

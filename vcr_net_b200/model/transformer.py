@@ -154,10 +154,11 @@ class Transformer(nn.Module):
                                             self.N),
                                     nn.Sequential(), nn.Sequential(), nn.Sequential())
 
-    def forward_tokens(self, src_tok, tgt_tok, add_input=False, want_head=False):
+    def forward_tokens(self, src_tok, tgt_tok, add_input=False, want_head=False, want_out=True):
         """want_head: also return (HeadPre src, HeadPre tgt) -- operand copies + squared norms of the outputs written by the
-        final LayerNorm kernel -- or None when the path does not produce them."""
-        return Fn.transformer_tokens(self, src_tok, tgt_tok, add_input=add_input, want_head=want_head)
+        final LayerNorm kernel -- or None when the path does not produce them.  want_out=False (with want_head): the fp32
+        outputs are not stored (returned as None) when the head only needs the operand copies."""
+        return Fn.transformer_tokens(self, src_tok, tgt_tok, add_input=add_input, want_head=want_head, want_out=want_out)
 
     def forward(self, *input):
         src_tok = ops.transpose_batched(input[0])

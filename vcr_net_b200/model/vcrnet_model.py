@@ -172,11 +172,14 @@ class VcpTopK(nn.Module):
         self.overlap2 = float(args.overlap2)
 
     def forward_tokens(self, src_tok, tgt_tok, src, tgt, pre=None):
+        """pre: (HeadPre src, HeadPre tgt) from the Transformer's final LayerNorm; the tokens may then be None."""
         if self.partial:
-            so, seo, to, teo, _, _ = Fn.vcp_select(src, src_tok, tgt, tgt_tok, self.overlap2, pre=pre)
+            so, seo, to, teo, _, _ = Fn.vcp_select(src, src_tok, tgt, tgt_tok, self.overlap2, pre=pre, want_tokens=False)
             s, c, _, _ = Fn.vcp_copair(so, seo, to, teo, self.overlap2)
             return s, c
-        return src, Fn.vcp_whole(src_tok.contiguous(), tgt_tok.contiguous(), tgt, pre=pre)
+        if src_tok is not None:
+            src_tok, tgt_tok = src_tok.contiguous(), tgt_tok.contiguous()
+        return src, Fn.vcp_whole(src_tok, tgt_tok, tgt, pre=pre)
 
     def forward(self, *input):
         src_tok = ops.transpose_batched(input[0])
@@ -309,12 +312,14 @@ class VCRNet(nn.Module):
             src_tok, tgt_tok = src_tok * 2.0, tgt_tok * 2.0
         elif isinstance(self.pointer, Transformer) and invariants is not None:
             want_head = isinstance(self.head, VcpTopK)
-            res = Fn.transformer_tokens_hoisted(self.pointer, invariants, want_head=want_head)
+            res = Fn.transformer_tokens_hoisted(self.pointer, invariants, want_head=want_head, want_out=stages is not None)
             src_tok, tgt_tok = res[0], res[1]
             pre = res[2] if want_head else None
         elif isinstance(self.pointer, Transformer):
             if isinstance(self.head, VcpTopK):     # the final LayerNorm also writes what the head derives from its output
-                src_tok, tgt_tok, pre = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True, want_head=True)
+                # (operand copy + squared norms); the fp32 copy is only stored when a caller asks for the stages
+                src_tok, tgt_tok, pre = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True, want_head=True,
+                                                                    want_out=stages is not None)
             else:
                 src_tok, tgt_tok = self.pointer.forward_tokens(src_tok, tgt_tok, add_input=True)   # :503-505
         if stages is not None:

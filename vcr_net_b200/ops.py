@@ -490,11 +490,12 @@ def layernorm(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e
     return out
 
 
-def layernorm_head(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, residual=None):
-    """layernorm(x) (+ residual) -> (out fp32, its "h3" Operand copy, its squared row norms), one kernel."""
+def layernorm_head(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, residual=None, want_out=True):
+    """layernorm(x) (+ residual) -> (out fp32 or None, its "h3" Operand copy, its squared row norms), one kernel.
+    want_out=False skips the fp32 store: the VCP head only reads the operand copy and the norms."""
     _chk(x, "x")
     M, D, ldx = _rows(x)
-    out = torch.empty(x.shape, dtype=_F32, device=x.device)
+    out = torch.empty(x.shape, dtype=_F32, device=x.device) if want_out else None
     op = Operand.empty(M, D, "h3", x.device)
     sq = torch.empty(x.shape[:-1], dtype=_F32, device=x.device)
     ldr = 0
@@ -502,7 +503,8 @@ def layernorm_head(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float
         _, _, ldr = _rows(residual)
     L = lib()
     L.check(L.vcr_layernorm_head(x.data_ptr(), ldx, a.data_ptr(), b.data_ptr(), float(eps), M, D,
-                                 residual.data_ptr() if residual is not None else None, ldr, out.data_ptr(), D,
+                                 residual.data_ptr() if residual is not None else None, ldr,
+                                 out.data_ptr() if out is not None else None, D,
                                  op.ptr, op.ld, op.plane_stride, sq.data_ptr(), _stream(x)), "vcr_layernorm_head")
     return out, op, sq
 
@@ -659,6 +661,33 @@ def rowsum_colsoftmax(pd, ld, Ns, Nt):
     L.check(L.vcr_rowsum_colsoftmax(pd.data_ptr(), ld, B, Ns, Nt, out.data_ptr(), ws.data_ptr(), ws.numel() * 4,
                                     _stream(pd)), "vcr_rowsum_colsoftmax")
     return out
+
+
+def select_stats(dot: torch.Tensor, ld: int, Ns: int, Nt: int, xx: torch.Tensor, yy: torch.Tensor):
+    """selectCom's two statistics from the score products dot [B,Ns,ld] (untouched): (row_stat [B,Ns], col_stat [B,Nt])."""
+    B = dot.shape[0]
+    dev = dot.device
+    L = lib()
+    row_stat = torch.empty((B, Ns), dtype=_F32, device=dev)
+    col_stat = torch.empty((B, Nt), dtype=_F32, device=dev)
+    wsb = L.vcr_select_stats_workspace_bytes(B, Ns, Nt)
+    ws = torch.empty(wsb // 4, dtype=_F32, device=dev)
+    L.check(L.vcr_select_stats(dot.data_ptr(), ld, B, Ns, Nt, xx.data_ptr(), yy.data_ptr(), row_stat.data_ptr(),
+                               col_stat.data_ptr(), ws.data_ptr(), wsb, _stream(dot)), "vcr_select_stats")
+    return row_stat, col_stat
+
+
+def gather_operand_rows(op: "Operand", sq: torch.Tensor, idx: torch.Tensor, B: int, Nin: int):
+    """Rows idx [B,K] of an "h3" Operand [B*Nin, C] and of its squared norms sq [B,Nin] -> (Operand [B*K, C], sq [B,K])."""
+    assert op.mode == "h3" and op.rows == B * Nin
+    K = idx.shape[1]
+    out = Operand.empty(B * K, op.cols, "h3", sq.device)
+    sq_out = torch.empty((B, K), dtype=_F32, device=sq.device)
+    L = lib()
+    L.check(L.vcr_gather_operand_rows(op.ptr, op.ld, op.plane_stride, B, Nin, idx.data_ptr(), K, op.cols, out.ptr, out.ld,
+                                      out.plane_stride, sq.data_ptr(), sq_out.data_ptr(), _stream(sq)),
+            "vcr_gather_operand_rows")
+    return out, sq_out
 
 
 def gather_rows(x_tok: torch.Tensor, idx: torch.Tensor):
