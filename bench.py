@@ -19,7 +19,8 @@ registers its own batch, no collective on the data path).
              staged reference travelled with the snapshot, else the torch-CPU port (oracle/vcr_oracle_torch.py, kind "port");
              `--impl reference` makes that the measured arm, at the GPU arm's batch size
   other_workloads   configs[0] (whole-to-whole, 1024 pts, batch 16, iter 1) with its own cpu_baseline; configs[3]
-             (4096 pts, 256 pairs split over the N ranks = strong scaling, in micro-batches of 32)
+             (4096 pts, 256 pairs split over the N ranks = strong scaling, in micro-batches of 32); configs[2] (LPD
+             pre-training forward + loss + hand-written backward, batch 16; e2e copies the loss back)
   variants   single-pass fp16 / bf16 tensor modes with the tolerance tests/test_gpu_parity.py asserts for them; batch-1
              latency
 """
@@ -577,9 +578,9 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         variants["latency_batch1"] = dict(lat, note="one pair per vcrnetIter call (all --iter iterations), device-resident inputs")
         # the other BASELINE configs, short, same timing rules
         a1 = argparse.Namespace(**vars(a)); a1.batch = 0; a1.num_points = 0
-        for wl in ("whole", "cfg4"):
+        for wl in ("whole", "cfg4", "lpd-train"):
             c2 = workload_cfg(a1, wl, world)
-            st2 = short if wl == "whole" else 3
+            st2 = 3 if wl == "cfg4" else short
             r2 = measure(c2, rank, world, dev, local_rank, st2, 3)
             v2, ms2 = pairs_per_s(r2, st2)
             e2, _ = pairs_per_s(r2, st2, "ms_e2e")

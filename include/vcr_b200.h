@@ -143,10 +143,17 @@ int vcr_edgeconv_dg(const float* PQ, int ldpq, const int* idx, int k, int N, lon
  * 1 = fp16, 2 = bf16.  ldpq, ld1 multiples of 4, slope >= 0. */
 int vcr_edgeconv_dg_tc(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts,
                        const float* W2, const float* b2, float slope, int mode, float* x1, int ld1,
-                       float* x2, int ld2, cudaStream_t stream);
+                       float* x2, int ld2, void* op1, void* op2, int ldop, long long op_plane, cudaStream_t stream);
 /* convSN1 + max (:130-132): out = act(max_k P[idx] + Q), C in {128,256,384,512}. */
 int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, const int* idx, int k, int N,
-                   long long total_pts, int C, float slope, float* out, int ldo, cudaStream_t stream);
+                   long long total_pts, int C, float slope, float* out, int ldo, void* op, int ldop,
+                   long long op_plane, cudaStream_t stream);
+/* op1 / op2 / op above (optional, NULL to skip): the same output rows also in "h3" operand format ([2 planes][rows][ldop]
+ * fp16 hi, lo * 2^11) for the GEMM that consumes them -- no separate vcr_to_operand pass over the LPDNet activations.
+ * vcr_lpd_point_mlp: conv1_lpd + conv2_lpd of model/lpdnet_model.py:111-112 in one kernel (bit-identical to vcr_conv3_act +
+ * vcr_gemm_f32), h1 optional, h2 fp32 + optional operand copy. */
+int vcr_lpd_point_mlp(const float* xyz, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                      float slope, float* h1, float* h2, void* op, int ldop, long long op_plane, cudaStream_t stream);
 
 /* ---- Transformer pieces: model/transformer.py -----------------------------------------------------
  * LayerNorm (:134-144): a*(x-mean)/(std_unbiased+eps)+b (+ residual if not NULL). D%128==0, D<=1024. */

@@ -626,6 +626,34 @@ def test_gather_operand_rows_matches_fp32_gather():
     want = ops.to_operand(rows.view(B * K, D), "h3")
     assert torch.equal(g_op.buf, want.buf) and torch.equal(g_sq, ops.sqnorm_rows(rows))
 
+
+def test_lpdnet_producers_write_operand_copies_bit_identically(net_whole):
+    """Round 2: conv1+conv2 fused (vcr_lpd_point_mlp) and the operand-format outputs of edgeconv_dg_tc / gather_max carry
+    exactly the bits of the unfused path (conv3_act + gemm, to_operand of the fp32 outputs)."""
+    rs = np.random.RandomState(3)
+    p = synth.make_pairs(2, 333, first_item=9)
+    xyz = cu(p["src"])
+    W = Fn.lpdnet_weights(net_whole.emb_nn)
+    for slope in (0.0, 0.2):
+        h1, h2, hop = ops.lpd_point_mlp(xyz, W["w1"], W["b1"], W["w2"], W["b2"], slope, want_h1=True, want_operand=True)
+        r1 = ops.conv3_act(xyz, W["w1"], W["b1"], slope)
+        r2 = ops.gemm(r1, W["w2"], W["b2"], act=1, slope=slope)
+        assert torch.equal(h1, r1) and torch.equal(h2, r2)
+        assert torch.equal(hop.buf, ops.to_operand(r2.view(-1, 64), "h3").buf)
+    B, N = 2, 333
+    pq = cu(rs.randn(B, N, 256).astype(np.float32))
+    idx = cu(rs.randint(0, N, size=(B, N, 20)).astype(np.int32))
+    x12 = torch.empty((B, N, 256), device=DEV)
+    cat_op = ops.Operand.empty(B * N, 512, "h3", DEV)
+    ops.edgeconv_dg_tc(pq, idx, W["dg2_w"], W["dg2_b"], 0.0, x12[:, :, 0:128], x12[:, :, 128:256], "h3",
+                       op1=cat_op.cols_view(0, 128), op2=cat_op.cols_view(128, 128))
+    want = ops.to_operand(x12.view(B * N, 256), "h3")
+    assert torch.equal(cat_op.buf[:, :, :256], want.buf[:, :, :256])
+    pq3 = cu(rs.randn(B, N, 512).astype(np.float32))
+    x3 = torch.empty((B, N, 256), device=DEV)
+    ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx, 0.0, x3, op=cat_op.cols_view(256, 256))
+    assert torch.equal(cat_op.buf[:, :, 256:512], ops.to_operand(x3.view(B * N, 256), "h3").buf[:, :, :256])
+
 # ---------------------------------------------------------------- tensor-core GEMM --------------------
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 520, 200), (4096, 1536, 512), (300, 64, 1024)])
 def test_gemm_tc_h3_matches_fp64(M, N, K):

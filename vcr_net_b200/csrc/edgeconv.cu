@@ -13,7 +13,7 @@
 //
 // Roofline: edgeconv_dg is FP32-FMA bound (2*128*128*k flops per point vs 4*(256+256)+4k bytes);
 // gather_max is L2/HBM bound: 4*k*C bytes read per point (L2 hits after the first touch) + 4*C write.
-#include "common.cuh"
+#include "tc_common.cuh"     // pack_h2 / lo_part (operand-format outputs)
 
 namespace {
 
@@ -134,7 +134,7 @@ __global__ void edge_max_kernel(const float* __restrict__ E, int k, long long to
 template <int VPL>
 __global__ void gather_max_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ Q, int ldq,
                                   const int* __restrict__ idx, int k, int N, long long total_pts, float slope,
-                                  float* __restrict__ out, int ldo) {
+                                  float* __restrict__ out, int ldo, __half* __restrict__ op, int ldop, long long op_plane) {
     const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pt >= total_pts) return;
@@ -162,6 +162,13 @@ __global__ void gather_max_kernel(const float* __restrict__ P, int ldp, const fl
         r.x = leaky(m[v].x + qq.x, slope); r.y = leaky(m[v].y + qq.y, slope);
         r.z = leaky(m[v].z + qq.z, slope); r.w = leaky(m[v].w + qq.w, slope);
         o[lane + v * 32] = r;
+        if (op != nullptr) {              // the same row in "h3" operand format for the next GEMM
+            __half* orow = op + pt * ldop + (lane + v * 32) * 4;
+            *reinterpret_cast<uint2*>(orow) = make_uint2(tc::pack_h2(r.x, r.y, 0), tc::pack_h2(r.z, r.w, 0));
+            *reinterpret_cast<uint2*>(orow + op_plane) =
+                make_uint2(tc::pack_h2(tc::lo_part(r.x, 0), tc::lo_part(r.y, 0), 0),
+                           tc::pack_h2(tc::lo_part(r.z, 0), tc::lo_part(r.w, 0), 0));
+        }
     }
 }
 
@@ -203,17 +210,20 @@ VCR_API int vcr_edgeconv_dg(const float* PQ, int ldpq, const int* idx, int k, in
 }
 
 VCR_API int vcr_gather_max(const float* P, int ldp, const float* Q, int ldq, const int* idx, int k, int N,
-                           long long total_pts, int C, float slope, float* out, int ldo, cudaStream_t stream) {
+                           long long total_pts, int C, float slope, float* out, int ldo, void* op, int ldop,
+                           long long op_plane, cudaStream_t stream) {
     VCR_REQUIRE(P && Q && idx && out && k > 0 && N > 0 && total_pts > 0);
+    if (op && ((ldop & 3) || (op_plane & 3) || (reinterpret_cast<uintptr_t>(op) & 7))) return VCR_ERR_INVALID;
+    __half* oph = reinterpret_cast<__half*>(op);
     if (slope < 0.f || C % 128 != 0 || C > 512) return VCR_ERR_UNSUPPORTED;
     if ((ldp & 3) || (ldq & 3) || (ldo & 3)) return VCR_ERR_INVALID;
     const int wpb = 8;
     const int grid = vcr_cdiv(total_pts, wpb);
     switch (C / 128) {
-        case 1: gather_max_kernel<1><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
-        case 2: gather_max_kernel<2><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
-        case 3: gather_max_kernel<3><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
-        case 4: gather_max_kernel<4><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo); break;
+        case 1: gather_max_kernel<1><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo, oph, ldop, op_plane); break;
+        case 2: gather_max_kernel<2><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo, oph, ldop, op_plane); break;
+        case 3: gather_max_kernel<3><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo, oph, ldop, op_plane); break;
+        case 4: gather_max_kernel<4><<<grid, wpb * 32, 0, stream>>>(P, ldp, Q, ldq, idx, k, N, total_pts, slope, out, ldo, oph, ldop, op_plane); break;
     }
     VCR_CHECK_LAUNCH();
     return VCR_OK;

@@ -69,7 +69,8 @@ template <int NTERMS, int FMT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 edgeconv_dg_tc_kernel(const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx, int N, long long total_pts,
                       const float* __restrict__ W2, const float* __restrict__ b2, float slope,
-                      float* __restrict__ x1, int ld1, float* __restrict__ x2, int ld2) {
+                      float* __restrict__ x1, int ld1, float* __restrict__ x2, int ld2,
+                      __half* __restrict__ op1, __half* __restrict__ op2, int ldop, long long op_plane) {
     using C_ = ECfg<NTERMS>;
     constexpr int PL = C_::PL;
     constexpr int obf = FMT;      // 1: bf16 operands
@@ -155,6 +156,13 @@ edgeconv_dg_tc_kernel(const float* __restrict__ PQ, int ldpq, const int* __restr
                     }
                 }
                 *reinterpret_cast<float4*>(x1 + pt * ld1 + lane * 4) = mx;
+                if (op1 != nullptr) {     // the same row in "h3" operand format (fp16 hi / lo * 2^11) for the next GEMM
+                    __half* orow = op1 + pt * ldop + lane * 4;
+                    *reinterpret_cast<uint2*>(orow) = make_uint2(tc::pack_h2(mx.x, mx.y, 0), tc::pack_h2(mx.z, mx.w, 0));
+                    *reinterpret_cast<uint2*>(orow + op_plane) =
+                        make_uint2(tc::pack_h2(tc::lo_part(mx.x, 0), tc::lo_part(mx.y, 0), 0),
+                                   tc::pack_h2(tc::lo_part(mx.z, 0), tc::lo_part(mx.w, 0), 0));
+                }
             }
             tc::fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core
             tc::mbar_arrive(&full[s]);
@@ -235,7 +243,15 @@ edgeconv_dg_tc_kernel(const float* __restrict__ PQ, int ldpq, const int* __restr
 #pragma unroll
                     for (int i = 1; i < KN; ++i) m = fmaxf(m, v[g * KN + i]);
                     const long long pt = tile * PTS_TILE + sub * PTS_SUB + g;
-                    if (pt < total_pts) x2[pt * ld2 + o] = leaky(m + bias, slope);
+                    if (pt < total_pts) {
+                        const float val = leaky(m + bias, slope);
+                        x2[pt * ld2 + o] = val;
+                        if (op2 != nullptr) {
+                            const __half hi = __float2half_rn(val);
+                            op2[pt * ldop + o] = hi;
+                            op2[pt * ldop + op_plane + o] = __float2half_rn((val - __half2float(hi)) * 2048.f);
+                        }
+                    }
                 }
             }
         }
@@ -247,7 +263,8 @@ edgeconv_dg_tc_kernel(const float* __restrict__ PQ, int ldpq, const int* __restr
 
 template <int NTERMS, int FMT>
 int launch_dg_tc(const float* PQ, int ldpq, const int* idx, int N, long long total_pts, const float* W2, const float* b2,
-                 float slope, float* x1, int ld1, float* x2, int ld2, cudaStream_t stream) {
+                 float slope, float* x1, int ld1, float* x2, int ld2, __half* op1, __half* op2, int ldop, long long op_plane,
+                 cudaStream_t stream) {
     using C_ = ECfg<NTERMS>;
     auto kern = edgeconv_dg_tc_kernel<NTERMS, FMT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
@@ -256,7 +273,7 @@ int launch_dg_tc(const float* PQ, int ldpq, const int* idx, int N, long long tot
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntiles = (total_pts + PTS_TILE - 1) / PTS_TILE;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    kern<<<grid, NTHREADS, C_::SMEM, stream>>>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2);
+    kern<<<grid, NTHREADS, C_::SMEM, stream>>>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, op1, op2, ldop, op_plane);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
@@ -267,13 +284,19 @@ int launch_dg_tc(const float* PQ, int ldpq, const int* idx, int N, long long tot
 // 1 = fp16, 2 = bf16 single pass.  k must be 20; ldpq, ld1 multiples of 4; PQ, x1 16-byte aligned.
 VCR_API int vcr_edgeconv_dg_tc(const float* PQ, int ldpq, const int* idx, int k, int N, long long total_pts,
                                const float* W2, const float* b2, float slope, int mode, float* x1, int ld1,
-                               float* x2, int ld2, cudaStream_t stream) {
+                               float* x2, int ld2, void* op1, void* op2, int ldop, long long op_plane,
+                               cudaStream_t stream) {
     VCR_REQUIRE(PQ && idx && W2 && b2 && x1 && x2 && N > 0 && total_pts > 0);
     if (k != KN || mode < 0 || mode > 2 || slope < 0.f) return VCR_ERR_UNSUPPORTED;
     if ((ldpq & 3) || (ld1 & 3) || (reinterpret_cast<uintptr_t>(PQ) & 15) || (reinterpret_cast<uintptr_t>(x1) & 15) ||
         (reinterpret_cast<uintptr_t>(W2) & 15))
         return VCR_ERR_INVALID;
-    if (mode == 0) return launch_dg_tc<3, 0>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, stream);
-    if (mode == 1) return launch_dg_tc<1, 0>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, stream);
-    return launch_dg_tc<1, 1>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, stream);
+    // optional "h3" operand-format copies of x1 / x2 (fp16 hi, lo * 2^11 planes; both or neither)
+    if ((op1 == nullptr) != (op2 == nullptr)) return VCR_ERR_INVALID;
+    if (op1 && ((ldop & 3) || (op_plane & 3) || (reinterpret_cast<uintptr_t>(op1) & 7))) return VCR_ERR_INVALID;
+    __half* o1 = reinterpret_cast<__half*>(op1);
+    __half* o2 = reinterpret_cast<__half*>(op2);
+    if (mode == 0) return launch_dg_tc<3, 0>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, o1, o2, ldop, op_plane, stream);
+    if (mode == 1) return launch_dg_tc<1, 0>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, o1, o2, ldop, op_plane, stream);
+    return launch_dg_tc<1, 1>(PQ, ldpq, idx, N, total_pts, W2, b2, slope, x1, ld1, x2, ld2, o1, o2, ldop, op_plane, stream);
 }

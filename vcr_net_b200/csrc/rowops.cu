@@ -49,6 +49,68 @@ __global__ void conv3_kernel(const float* __restrict__ xyz, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// conv1_lpd + conv2_lpd fused (model/lpdnet_model.py:111-112): xyz [B,3,N] -> h1 = act(W1 x + b1) [B*N,64] (optional store),
+// h2 = act(W2 h1 + b2) [B*N,64] fp32 and, optionally, h2 in "h3" operand format for the kNN prefilter / the DG1 GEMM.
+// A warp owns 32 points (lane = point), W2 is read from shared memory as broadcast float4.  Arithmetic is the two separate
+// kernels' (conv3_kernel: w0*x, fma, fma, + b; sgemm_kernel: one fma chain over k = 0..63 starting at 0, then + b), so h1 / h2
+// are bit-identical to the unfused path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lpd_point_mlp_kernel(const float* __restrict__ xyz, const float* __restrict__ w1, const float* __restrict__ b1,
+                     const float* __restrict__ w2, const float* __restrict__ b2, int N, float slope,
+                     float* __restrict__ h1o, float* __restrict__ h2o, __half* __restrict__ op, int ldop, long long op_plane) {
+    __shared__ __align__(16) float sw2[64 * 64];
+    __shared__ float sw1[64 * 3], sb1[64], sb2[64];
+    for (int e = threadIdx.x; e < 64 * 64; e += 128) sw2[e] = w2[e];
+    for (int e = threadIdx.x; e < 64 * 3; e += 128) sw1[e] = w1[e];
+    if (threadIdx.x < 64) { sb1[threadIdx.x] = b1[threadIdx.x]; sb2[threadIdx.x] = b2[threadIdx.x]; }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float* p = xyz + (size_t)b * 3 * N;
+    const float x = p[n], y = p[N + n], z = p[2 * N + n];
+    float h1[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        float acc = sw1[c * 3 + 0] * x;
+        acc = fmaf(sw1[c * 3 + 1], y, acc);
+        acc = fmaf(sw1[c * 3 + 2], z, acc);
+        h1[c] = leaky(acc + sb1[c], slope);
+    }
+    const size_t row = (size_t)b * N + n;
+    if (h1o != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 64; c += 4)
+            *reinterpret_cast<float4*>(h1o + row * 64 + c) = make_float4(h1[c], h1[c + 1], h1[c + 2], h1[c + 3]);
+    }
+#pragma unroll 1
+    for (int o0 = 0; o0 < 64; o0 += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k4 = 0; k4 < 64; k4 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 w = *reinterpret_cast<const float4*>(sw2 + (o0 + u) * 64 + k4);
+                acc[u] = fmaf(h1[k4 + 0], w.x, acc[u]); acc[u] = fmaf(h1[k4 + 1], w.y, acc[u]);
+                acc[u] = fmaf(h1[k4 + 2], w.z, acc[u]); acc[u] = fmaf(h1[k4 + 3], w.w, acc[u]);
+            }
+        }
+        float4 r;
+        r.x = leaky(acc[0] + sb2[o0 + 0], slope); r.y = leaky(acc[1] + sb2[o0 + 1], slope);
+        r.z = leaky(acc[2] + sb2[o0 + 2], slope); r.w = leaky(acc[3] + sb2[o0 + 3], slope);
+        *reinterpret_cast<float4*>(h2o + row * 64 + o0) = r;
+        if (op != nullptr) {
+            __half* orow = op + row * ldop + o0;
+            *reinterpret_cast<uint2*>(orow) = make_uint2(tc::pack_h2(r.x, r.y, 0), tc::pack_h2(r.z, r.w, 0));
+            *reinterpret_cast<uint2*>(orow + op_plane) =
+                make_uint2(tc::pack_h2(tc::lo_part(r.x, 0), tc::lo_part(r.y, 0), 0),
+                           tc::pack_h2(tc::lo_part(r.z, 0), tc::lo_part(r.w, 0), 0));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm of model/transformer.py:141-144: a*(x-mean)/(std_unbiased+eps)+b.  D % 128 == 0, D <= 1024.
 // ---------------------------------------------------------------------------------------------
 // EXTRA: also write the row in operand format (fp16 hi / lo * 2^11 planes) and its squared norm -- the two things the
@@ -708,6 +770,18 @@ VCR_API int vcr_conv3_act(const float* xyz, const float* w, const float* bias, i
 }
 
 // out = a*(x-mean)/(std_unbiased+eps)+b (+ residual when residual != NULL)
+// conv1_lpd + conv2_lpd (+ operand copy of the result): xyz [B,3,N]; w1 [64,3], w2 [64,64] row-major; h1 (nullable) / h2 [B*N,64];
+// op (nullable): "h3" operand planes [2][B*N][ldop] of h2.
+VCR_API int vcr_lpd_point_mlp(const float* xyz, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                              float slope, float* h1, float* h2, void* op, int ldop, long long op_plane, cudaStream_t stream) {
+    VCR_REQUIRE(xyz && w1 && b1 && w2 && b2 && h2 && B > 0 && N > 0 && B <= 65535);
+    if (op && ((ldop & 3) || (op_plane & 3) || (reinterpret_cast<uintptr_t>(op) & 7))) return VCR_ERR_INVALID;
+    dim3 g(vcr_cdiv(N, 128), B);
+    lpd_point_mlp_kernel<<<g, 128, 0, stream>>>(xyz, w1, b1, w2, b2, N, slope, h1, h2, reinterpret_cast<__half*>(op), ldop, op_plane);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
 VCR_API int vcr_layernorm(const float* x, int ldx, const float* a, const float* b, float eps, long long M, int D,
                           const float* residual, int ldr, float* out, int ldo, cudaStream_t stream) {
     VCR_REQUIRE(x && a && b && out && M > 0);

@@ -96,15 +96,20 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
         trans = transform_net_matrix(m.t_net3d, xyz)
         xyz_in = ops.rigid_apply(xyz, trans.transpose(1, 2).contiguous(),
                                  torch.zeros((B, 3), dtype=_F32, device=xyz.device))
-    h1 = ops.conv3_act(xyz_in, W["w1"], W["b1"], slope)                      # :111
-    h2 = ops.gemm(h1, W["w2"], W["b2"], act=1, slope=slope)                  # :112  [B,N,64]
-    if m.tfea:                                                               # :114-118  per-cloud [N,64] x [64,64]
-        trans_feat = transform_net_matrix(m.t_net_fea, h2)
-        h2t = torch.empty_like(h2)
-        ops.bgemm(h2, 64, N * 64, 0, trans_feat, 64, 64 * 64, 0, 1, h2t, 64, N * 64, 0, N, 64, 64, B, 1)
-        h2 = h2t
     tc = config.precision != "fp32"
-    h2_op = ops.to_operand(h2.view(B * N, 64), "h3") if tc else None         # shared by the kNN prefilter and the DG1 GEMM
+    fused_ops = tc and not m.tfea            # producers write the "h3" operand copies their consumers read (no to_operand passes)
+    if fused_ops and W["w1"].shape[0] == 64:
+        h1, h2, h2_op = ops.lpd_point_mlp(xyz_in, W["w1"], W["b1"], W["w2"], W["b2"], slope,
+                                          want_h1=stages is not None, want_operand=True)      # :111-112
+    else:
+        h1 = ops.conv3_act(xyz_in, W["w1"], W["b1"], slope)                  # :111
+        h2 = ops.gemm(h1, W["w2"], W["b2"], act=1, slope=slope)              # :112  [B,N,64]
+        if m.tfea:                                                           # :114-118  per-cloud [N,64] x [64,64]
+            trans_feat = transform_net_matrix(m.t_net_fea, h2)
+            h2t = torch.empty_like(h2)
+            ops.bgemm(h2, 64, N * 64, 0, trans_feat, 64, 64 * 64, 0, 1, h2t, 64, N * 64, 0, N, 64, 64, B, 1)
+            h2 = h2t
+        h2_op = ops.to_operand(h2.view(B * N, 64), "h3") if tc else None     # shared by the kNN prefilter and the DG1 GEMM
     if idx_feat is None:                                                     # :122 (feature-space kNN)
         if config.use_knn_tc(N) and ops.knn_tc_supported(64, k):
             idx_feat = ops.knn_topk_tc(h2, h2_op, k)
@@ -118,27 +123,32 @@ def lpdnet_tokens(m, xyz: torch.Tensor, idx_feat=None, idx_xyz=None, stages=None
     else:
         pq1 = ops.gemm(h2, W["dg1_w"], W["dg1_b"])                           # [B,N,256] = [P|Q]
     cat = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
+    mode = config.precision
+    # the conv3 GEMM's A operand [x1 | x2 | x3]: in the parity mode each producer writes its slice in operand format
+    cat_op = ops.Operand.empty(B * N, 512, "h3", xyz.device) if mode == "h3" else None
     if config.precision == "fp32":
         ops.edgeconv_dg(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256])  # :123-126
     else:
         ops.edgeconv_dg_tc(pq1, idx_feat, W["dg2_w"], W["dg2_b"], slope, cat[:, :, 0:128], cat[:, :, 128:256],
-                           config.precision)
+                           config.precision, op1=cat_op.cols_view(0, 128) if cat_op is not None else None,
+                           op2=cat_op.cols_view(128, 128) if cat_op is not None else None)
     if idx_xyz is None:
         idx_xyz = ops.knn_topk(xyz, k, token_major=False)                    # :129 (3-d kNN)
     if tc:
         pq3 = torch.empty((B, N, 512), dtype=_F32, device=xyz.device)
-        ops.gemm_tc(ops.to_operand(cat[:, :, 128:256], "h3"), wpq[1], B * N, 512, 128, bias=W["sn1_b"], c=pq3)
+        x2_op = cat_op.cols_view(128, 128) if cat_op is not None else ops.to_operand(cat[:, :, 128:256], "h3")
+        ops.gemm_tc(x2_op, wpq[1], B * N, 512, 128, bias=W["sn1_b"], c=pq3)
     else:
         pq3 = ops.gemm(cat[:, :, 128:256], W["sn1_w"], W["sn1_b"])           # [B,N,512] = [P3|Q3]
-    ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_xyz, slope, cat[:, :, 256:512])  # :130-132
-    mode = config.precision
+    ops.gather_max(pq3[:, :, 0:256], pq3[:, :, 256:512], idx_xyz, slope, cat[:, :, 256:512],
+                   op=cat_op.cols_view(256, 256) if cat_op is not None else None)               # :130-132
     if mode == "fp32":
         emb = ops.gemm(cat, W["w3"], W["b3"], act=1, slope=slope, out=out)   # :134-135
     else:
         w3 = packed(m, "w3_" + mode, [m.conv3_lpd.weight], lambda: ops.to_operand(W["w3"], mode))
         emb = out if out is not None else torch.empty((B, N, W["w3"].shape[0]), dtype=_F32, device=xyz.device)
-        ops.gemm_tc(ops.to_operand(cat, mode), w3, B * N, W["w3"].shape[0], 512, bias=W["b3"], act=1,
-                    slope=slope, c=emb)
+        ops.gemm_tc(cat_op if cat_op is not None else ops.to_operand(cat, mode), w3, B * N, W["w3"].shape[0], 512,
+                    bias=W["b3"], act=1, slope=slope, c=emb)
     if stages is not None:
         stages.update(f64=h2, idx_feat=idx_feat, idx_xyz=idx_xyz, cat=cat, h1=h1, pq1=pq1, pq3=pq3)
         if m.t3d:

@@ -358,27 +358,55 @@ def edgeconv_dg(pq: torch.Tensor, idx: torch.Tensor, w2: torch.Tensor, b2: torch
 
 
 def edgeconv_dg_tc(pq: torch.Tensor, idx: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, slope: float,
-                   x1: torch.Tensor, x2: torch.Tensor, mode: str):
-    """edgeconv_dg on tcgen05 tensor cores (csrc/edgeconv_tc.cu); mode in TC_MODES."""
+                   x1: torch.Tensor, x2: torch.Tensor, mode: str, op1: "Operand | None" = None, op2: "Operand | None" = None):
+    """edgeconv_dg on tcgen05 tensor cores (csrc/edgeconv_tc.cu); mode in TC_MODES.
+    op1 / op2: optional "h3" Operand views (same buffer) that also receive x1 / x2 in operand format."""
     B, N, _ = pq.shape
     _, _, ldpq = _rows(pq)
     _, _, ld1 = _rows(x1)
     _, _, ld2 = _rows(x2)
+    if op1 is not None:
+        assert op1.mode == "h3" and op2.mode == "h3" and op1.ld == op2.ld and op1.plane_stride == op2.plane_stride
     L = lib()
     L.check(L.vcr_edgeconv_dg_tc(pq.data_ptr(), ldpq, idx.data_ptr(), idx.shape[2], N, B * N, w2.data_ptr(),
                                  b2.data_ptr(), float(slope), TC_MODES[mode], x1.data_ptr(), ld1, x2.data_ptr(), ld2,
+                                 op1.ptr if op1 is not None else None, op2.ptr if op2 is not None else None,
+                                 op1.ld if op1 is not None else 0, op1.plane_stride if op1 is not None else 0,
                                  _stream(pq)), "vcr_edgeconv_dg_tc")
 
 
-def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float, out: torch.Tensor):
-    """out[b,n,:] = act(max_k p[b, idx[b,n,k], :] + q[b,n,:]); p, q, out are [B,N,C] row views."""
+def gather_max(p: torch.Tensor, q: torch.Tensor, idx: torch.Tensor, slope: float, out: torch.Tensor,
+               op: "Operand | None" = None):
+    """out[b,n,:] = act(max_k p[b, idx[b,n,k], :] + q[b,n,:]); p, q, out are [B,N,C] row views.
+    op: optional "h3" Operand view that also receives the rows in operand format."""
     B, N, C = p.shape
     _, _, ldp = _rows(p)
     _, _, ldq = _rows(q)
     _, _, ldo = _rows(out)
     L = lib()
     L.check(L.vcr_gather_max(p.data_ptr(), ldp, q.data_ptr(), ldq, idx.data_ptr(), idx.shape[2], N, B * N, C,
-                             float(slope), out.data_ptr(), ldo, _stream(p)), "vcr_gather_max")
+                             float(slope), out.data_ptr(), ldo, op.ptr if op is not None else None,
+                             op.ld if op is not None else 0, op.plane_stride if op is not None else 0, _stream(p)),
+            "vcr_gather_max")
+
+
+def lpd_point_mlp(xyz: torch.Tensor, w1, b1, w2, b2, slope: float, want_h1: bool = True, want_operand: bool = False):
+    """conv1_lpd + conv2_lpd (model/lpdnet_model.py:111-112) in one kernel: xyz [B,3,N] -> (h1 [B,N,64] or None, h2 [B,N,64],
+    "h3" Operand of h2 or None); bit-identical to conv3_act + gemm."""
+    _chk(xyz, "xyz")
+    xyz = xyz.contiguous()
+    B, _, N = xyz.shape
+    assert tuple(w1.shape) == (64, 3) and tuple(w2.shape) == (64, 64)
+    dev = xyz.device
+    h1 = torch.empty((B, N, 64), dtype=_F32, device=dev) if want_h1 else None
+    h2 = torch.empty((B, N, 64), dtype=_F32, device=dev)
+    op = Operand.empty(B * N, 64, "h3", dev) if want_operand else None
+    L = lib()
+    L.check(L.vcr_lpd_point_mlp(xyz.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), B, N, float(slope),
+                                h1.data_ptr() if want_h1 else None, h2.data_ptr(), op.ptr if op is not None else None,
+                                op.ld if op is not None else 0, op.plane_stride if op is not None else 0, _stream(xyz)),
+            "vcr_lpd_point_mlp")
+    return h1, h2, op
 
 
 def edge_max(e: torch.Tensor, k: int, out: torch.Tensor):
