@@ -295,6 +295,21 @@ def test_softmax_colsum_topk():
     assert np.array_equal(nump(idx), O.topk_desc(vals[:, :494], 196))
 
 
+@pytest.mark.parametrize("n,K", [(21, 20), (32, 7), (100, 64), (333, 200), (1024, 1024), (1500, 700), (4096, 2408)])
+def test_topk_select_sizes_and_ties(n, K):
+    """vcr_topk_select on both kernels (one key per thread with warp shuffles for n <= 1024, the shared-memory network above):
+    sorted indices with ties broken by lower index, and the membership mask."""
+    rs = np.random.RandomState(n + K)
+    vals = np.round(rs.randn(5, n), 1).astype(np.float32)             # rounding => many ties
+    vals[0, : n // 2] = 0.5                                           # one row dominated by a single tied value
+    idx, mask = ops.topk_select(cu(vals), K, want_idx=True, want_mask=True)
+    want = O.topk_desc(vals, K)
+    assert np.array_equal(nump(idx), want)
+    wm = np.zeros_like(vals, dtype=np.uint8)
+    np.put_along_axis(wm, want, 1, axis=1)
+    assert np.array_equal(nump(mask), wm)
+
+
 def test_attention_vs_golden():
     g = load_golden("attention")
     q, k, v = g["q"], g["k"], g["v"]

@@ -44,6 +44,44 @@ __global__ void topk_sort_kernel(const float* __restrict__ vals, int n, int npad
     }
 }
 
+// npad <= 1024: one key per thread.  Compare-exchange partners closer than a warp are reached with shuffles, the 15 stages
+// with stride >= 32 go through double-buffered shared memory (one barrier each): 15 barriers instead of 55.  Same network,
+// same result as topk_sort_kernel.
+__global__ void __launch_bounds__(1024)
+topk_sort_warp_kernel(const float* __restrict__ vals, int n, int npad, int K, int* __restrict__ idx_out,
+                      uint8_t* __restrict__ mask_out) {
+    __shared__ unsigned long long xch[2][1024];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* v = vals + (size_t)b * n;
+    unsigned long long key = tid < n ? (((unsigned long long)float_desc_key(v[tid]) << 32) | (unsigned int)tid) : ~0ull;
+    int buf = 0;
+    for (int size = 2; size <= npad; size <<= 1) {
+        const bool up = (tid & size) == 0;
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            unsigned long long other;
+            if (stride >= 32) {
+                xch[buf][tid] = key;
+                __syncthreads();
+                other = xch[buf][tid ^ stride];
+                buf ^= 1;                                  // the next smem stage writes the other buffer: no second barrier
+            } else {
+                other = __shfl_xor_sync(0xffffffffu, key, stride);
+            }
+            const bool lower = (tid & stride) == 0;
+            const bool take_min = lower == up;
+            key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+        }
+    }
+    if (mask_out)
+        for (int i = tid; i < n; i += blockDim.x) mask_out[(size_t)b * n + i] = 0;
+    __syncthreads();
+    if (tid < K) {
+        const int i = (int)(key & 0xffffffffu);
+        if (idx_out) idx_out[(size_t)b * K + tid] = i;
+        if (mask_out) mask_out[(size_t)b * n + i] = 1;
+    }
+}
+
 }  // namespace
 
 // vals [B,n] -> idx_out [B,K] (sorted, optional) and/or mask_out [B,n] uint8 (1 = selected, optional)
@@ -52,6 +90,11 @@ VCR_API int vcr_topk_select(const float* vals, int B, int n, int K, int* idx_out
     VCR_REQUIRE(vals && (idx_out || mask_out) && B > 0 && n > 0 && K > 0 && K <= n);
     int npad = 2;
     while (npad < n) npad <<= 1;
+    if (npad >= 32 && npad <= 1024) {
+        topk_sort_warp_kernel<<<B, npad, 0, stream>>>(vals, n, npad, K, idx_out, mask_out);
+        VCR_CHECK_LAUNCH();
+        return VCR_OK;
+    }
     const size_t smem = (size_t)npad * sizeof(unsigned long long);
     if (smem > 224 * 1024) return VCR_ERR_UNSUPPORTED;
     if (smem > 48 * 1024 &&
