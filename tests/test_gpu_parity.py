@@ -985,6 +985,26 @@ def test_vcrnet_iter_hoisting_is_bit_identical(net_partial, net_whole, which):
             assert torch.equal(a, b), level
 
 
+def test_vcrnet_iter_hoisting_two_blocks_is_bit_identical():
+    """--n_blocks 2 (util/initPara.py:176): only decoder layer 0's self-attention on tgt is loop-invariant, the K / V
+    projections of encoder(tgt) are hoisted for every decoder layer; same bits as the plain loop."""
+    from vcr_net_b200 import config
+    torch.manual_seed(5)
+    net = V.VCRNet(default_args(partial=True, overlap2=synth.OVERLAP2_0575, n_blocks=2)).to(DEV).eval()
+    p = synth.make_pairs(2, 384, partial=True, first_item=44)
+    src, tgt = cu(p["src"]), cu(p["tgt"])
+    old = config.hoist
+    try:
+        config.hoist = "none"
+        base = V.vcrnetIter(net, src, tgt, iter=2)
+        config.hoist = "all"
+        hoisted = V.vcrnetIter(net, src, tgt, iter=2)
+    finally:
+        config.hoist = old
+    for a, b in zip(base, hoisted):
+        assert torch.equal(a, b)
+
+
 def test_attention_probabilities_recorded_on_request(net_whole):
     """MultiHeadedAttention.attn (model/transformer.py:216-219, plot-only) is opt-in: module.record_attn = True fills it
     with the head-summed probabilities [B, Nq, Nk]; rows sum to the number of heads."""
