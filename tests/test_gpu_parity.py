@@ -739,9 +739,10 @@ def _attn_operands(q, k, v, mode):
     return ops.to_operand(tok(q), mode), ops.to_operand(tok(k), mode), ops.to_operand(vt, mode)
 
 
-@pytest.fixture(params=[2, 4])
+@pytest.fixture(params=[1, 2, 4], ids=["tile-ping-pong", "8-warps-per-tile", "16-warps-per-tile"])
 def flash_warps(request):
-    """Both softmax-warp layouts of the flash attention kernel (8 / 16 softmax warps per CTA)."""
+    """The softmax organisations of the flash attention kernel: two groups of 4 warps alternating key tiles (default), 8 or
+    16 warps on every tile."""
     old = ops.set_flash_warps(request.param)
     yield request.param
     ops.set_flash_warps(old)

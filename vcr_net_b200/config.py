@@ -68,8 +68,9 @@ gemm_pair = os.environ.get("VCR_GEMM_PAIR", "auto")
 GEMM_PAIR_CODES = {"0": 0, "1": 1, "auto": 2}
 
 
-# flash attention: softmax warps per TMEM lane quarter (2: 8 softmax warps / 384 threads per CTA, 4: 16 / 640); applied to
-# the library when it is loaded, switchable with ops.set_flash_warps()
+# flash attention softmax organisation: 2 (default) = 8 softmax warps on every key tile (384 threads per CTA), 4 = 16 (640),
+# 1 = two groups of 4 warps alternating key tiles (measured slower in the parity mode); applied to the library when it is
+# loaded, switchable with ops.set_flash_warps()
 flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "2"))
 
 

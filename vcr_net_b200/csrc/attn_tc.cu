@@ -84,7 +84,7 @@ __device__ __forceinline__ int ordered_key(float f) { const int b = __float_as_i
 __device__ __forceinline__ float ordered_val(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 constexpr int kNegInfKey = (int)0x807fffffu;         // ordered_key(-inf)
 
-template <int NTERMS, int FMT, int NWQ>
+template <int NTERMS, int FMT, int NWQ, bool PING>
 __global__ void __launch_bounds__(128 + 128 * NWQ, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -116,9 +116,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
             tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], 128 * NWQ);
+            tc::mbar_init(&s_full[s], 1);  tc::mbar_init(&s_empty[s], PING ? 128 : 128 * NWQ);
         }
-        tc::mbar_init(p_full, 128 * NWQ); tc::mbar_init(p_empty, 1);
+        tc::mbar_init(p_full, PING ? 128 : 128 * NWQ); tc::mbar_init(p_empty, 1);
         tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 128 * NWQ);
         tc::fence_barrier_init();
     }
@@ -239,6 +239,193 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 tc::umma_commit(o_full);
             }
+        }
+    } else if (PING && warp >= 4) {
+        // ============================== softmax + output, two groups alternating key tiles ==============================
+        // The per-tile softmax is a chain of dependent hand-offs (S ready -> TMEM load -> max -> exp2 -> P store -> fence ->
+        // mbarrier -> MMA issue -> commit -> P buffer free ...), and with every softmax warp on the SAME tile that chain,
+        // ~2x the tile's tensor time, set the tile period (ncu: tensor pipe 42-49 % active, issue slots 32 %).  Here the 8
+        // warps form two groups of 4 (one warp per TMEM lane quarter, a thread owns a whole 64-key row of the tile: no
+        // column split, no per-tile exchange barrier); group g takes tiles j = g, g+2, ...  The only per-tile dependence
+        // between consecutive tiles is the running reference maximum: the owner of tile j publishes it right after its row
+        // maximum is known (named barrier arrive), the owner of tile j+1 picks it up (named barrier sync) -- so tile j+1's
+        // TMEM load and maximum overlap tile j's exp2 / split / P store, and its P store only waits for P V_j.
+        // Each group keeps its own partial row sum l relative to the maximum it last saw; the partials are brought to the
+        // final maximum and added once per item.
+        constexpr int OW = DK / 2;                    // O columns per warp at write-out
+        const int qq = warp & 3, grp = (warp - 4) >> 2;
+        const int rloc = qq * 32 + lane;
+        const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
+        const int obf = p.out_bf16;
+        uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
+        float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // [0,128): reference maximum, [128,384): l exchange
+        auto quarter_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory"); };
+        // turn hand-off between the two warps of a lane quarter: ids 5.. (group 0 -> 1), 9.. (group 1 -> 0)
+        auto turn_arrive = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(5 + 4 * grp + qq) : "memory"); };
+        auto turn_wait = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(5 + 4 * (grp ^ 1) + qq) : "memory"); };
+        uint32_t w = 0, gbase = 0;
+        for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w, gbase += (uint32_t)nkv) {
+            const int qt = (int)(it % nqt);
+            const int bh = (int)(it / nqt);
+            const int hh = bh % p.H, b = bh / p.H;
+            const uint8_t* keep = p.keep ? p.keep + (size_t)b * p.Nk : nullptr;
+            float m_seen = 0.f, l = 0.f;
+            bool seen = false;
+            for (int j = grp; j < nkv; j += 2) {
+                const uint32_t g = gbase + (uint32_t)j;
+                const int sb = g & 1;
+                uint32_t km0 = 0xffffffffu, km1 = 0xffffffffu;
+                if (keep != nullptr) {
+                    const int key = j * BKV + lane;
+                    km0 = __ballot_sync(0xffffffffu, key < p.Nk && __ldg(keep + key) != 0);
+                    km1 = __ballot_sync(0xffffffffu, key + 32 < p.Nk && __ldg(keep + key + 32) != 0);
+                }
+                tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
+                tc::tc_fence_after();
+                float s[BKV];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr + h * 32;
+                    uint32_t r0[32];
+                    tc::tmem_ld_32x32(sa, r0);
+                    if (NTERMS == 3) {
+                        uint32_t r1[32];
+                        tc::tmem_ld_32x32(sa + BKV, r1);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s[h * 32 + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
+                    } else {
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(r0[i]);
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2
+                // ---- (mask,) row maximum of the tile ----
+                float sc = p.scale_log2;
+                if (keep != nullptr || j * BKV + BKV > p.Nk) {    // warp-uniform: ragged or masked tile
+#pragma unroll
+                    for (int i = 0; i < BKV; ++i) {
+                        float x = s[i] * sc;
+                        const int key = j * BKV + i;
+                        const uint32_t km = i < 32 ? km0 : km1;
+                        if (key >= p.Nk) x = -INFINITY;
+                        else if (!((km >> (i & 31)) & 1u)) x = -1e9f * kLog2e;
+                        s[i] = x;
+                    }
+                    sc = 1.f;
+                }
+                float mt = s[0];
+#pragma unroll
+                for (int i = 1; i < BKV; ++i) mt = fmaxf(mt, s[i]);
+                mt *= sc;                                         // sc > 0
+                // ---- my turn: reference maximum (lazy: it only moves when exceeded by more than 2^8) ----
+                float m_ref = mt, o_factor = 1.f;
+                bool need = false;
+                if (j > 0) {
+                    turn_wait();
+                    const float m_prev = xch[rloc];
+                    if (mt > m_prev + kRescaleThreshold) { o_factor = ex2_approx(m_prev - mt); need = true; }
+                    else m_ref = m_prev;
+                }
+                if (j + 1 < nkv) { xch[rloc] = m_ref; turn_arrive(); }
+                if (seen && m_seen != m_ref) l *= ex2_approx(m_seen - m_ref);     // my partial sum follows the reference
+                m_seen = m_ref; seen = true;
+                const float neg_m = -m_ref;
+                float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < BKV; i += 2) {
+                    s[i] = ex2_approx(fmaf(s[i], sc, neg_m));         rs0 += s[i];
+                    s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m)); rs1 += s[i + 1];
+                }
+                l += rs0 + rs1;
+                // ---- P buffer free (P V of the previous tile retired), also the point where O may be touched ----
+                tc::mbar_wait(p_empty, (g & 1) ^ 1);
+                if (__any_sync(0xffffffffu, need)) {
+                    tc::tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < PL * DK; c += 32) {       // all of this lane quarter's O columns (D0, and D1)
+                        const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + c;
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32(oa, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * o_factor);
+                        tmem_st_32x32(oa, r);
+                    }
+                    tmem_st_wait();
+                    tc::tc_fence_before();
+                }
+                // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: 8 16-byte chunks per plane ----
+#pragma unroll
+                for (int c = 0; c < BKV / 8; ++c) {
+                    const int pos = (c ^ (rloc & 7)) * 16;
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) wv[q] = tc::pack_h2(s[c * 8 + 2 * q], s[c * 8 + 2 * q + 1], obf);
+                    *reinterpret_cast<uint4*>(p_smem + pos) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    if (NTERMS == 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            wv[q] = tc::pack_h2(tc::lo_part(s[c * 8 + 2 * q], obf), tc::lo_part(s[c * 8 + 2 * q + 1], obf), obf);
+                        *reinterpret_cast<uint4*>(p_smem + C_::P_TILE + pos) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+                tc::fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
+                tc::mbar_arrive(p_full);
+            }
+            // ---- item done: bring both partial sums to the final reference maximum (the last tile's), add them ----
+            if (((nkv - 1) & 1) == grp) xch[rloc] = m_seen;       // owner of the last tile
+            quarter_bar();
+            const float m_fin = xch[rloc];
+            if (seen && m_seen != m_fin) l *= ex2_approx(m_seen - m_fin);
+            xch[128 + grp * 128 + rloc] = l;
+            quarter_bar();
+            l = xch[128 + rloc] + xch[256 + rloc];
+            quarter_bar();                                        // the exchange area is reused by the next item
+            tc::mbar_wait(o_full, w & 1);
+            tc::tc_fence_after();
+            const int q = qt * BQ + rloc;
+            const bool q_ok = q < p.Nq;
+            const float inv_l = 1.f / l;
+            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + grp * OW;
+            __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK + grp * OW;
+#pragma unroll 1
+            for (int c = 0; c < OW; c += 32) {
+                uint32_t r0[32];
+                float v[32];
+                tc::tmem_ld_32x32(oa + c, r0);
+                if (NTERMS == 3) {
+                    uint32_t r1[32];
+                    tc::tmem_ld_32x32(oa + DK + c, r1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
+                } else {
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * inv_l;
+                }
+                if (q_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wv[t] = tc::pack_h2(v[i + 2 * t], v[i + 2 * t + 1], obf);
+                        *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        if (NTERMS == 3) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                wv[t] = tc::pack_h2(tc::lo_part(v[i + 2 * t], obf), tc::lo_part(v[i + 2 * t + 1], obf), obf);
+                            *reinterpret_cast<uint4*>(orow + p.o_plane + c + i) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        }
+                    }
+                }
+            }
+            if (p.lse && q_ok && grp == 0) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_fin + log2f(l);
+            tc::tc_fence_before();
+            tc::mbar_arrive(o_empty);
         }
     } else if (warp >= 4) {
         // ============================== softmax + output ==============================
@@ -447,10 +634,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
 }
 
-template <int NTERMS, int FMT, int NWQ>
+template <int NTERMS, int FMT, int NWQ, bool PING = false>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
     using C_ = ACfg<NTERMS>;
-    auto kern = flash_attn_tc_kernel<NTERMS, FMT, NWQ>;
+    auto kern = flash_attn_tc_kernel<NTERMS, FMT, NWQ, PING>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -466,10 +653,13 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 static std::atomic<int> g_vcr_flash_warps{2};      // tuning knob (see vcr_set_flash_warps)
 
-// Softmax warps per TMEM lane quarter of the flash attention kernel: 2 (8 softmax warps, 384 threads) or 4 (16 warps,
-// 640 threads).  Process-wide; returns the previous setting.  Results agree to fp32 rounding of the row sums.
+// Softmax organisation of the flash attention kernel: 2 (default) = 8 warps on every tile, two per TMEM lane quarter
+// splitting the key columns (384 threads); 4 = 16 warps, four per quarter (640 threads); 1 = two groups of 4 warps
+// alternating key tiles, a thread owning a whole 64-key row of its tile (built in round 2 to overlap consecutive tiles'
+// softmax chains; measured 0.90-0.95x in the parity mode, 1.04x in single-pass fp16 -- profiles/r02_flash_organisations.txt
+// -- so it is not the default).  Process-wide; returns the previous setting.  Results agree to fp32 rounding of the row sums.
 VCR_API int vcr_set_flash_warps(int nwq) {
-    return g_vcr_flash_warps.exchange(nwq == 4 ? 4 : 2);
+    return g_vcr_flash_warps.exchange(nwq == 4 ? 4 : (nwq == 2 ? 2 : 1));
 }
 
 // Q: operand buffer [planes][B*Nq][ldq], head hh in columns [hh*128, hh*128+128) of the given base;
@@ -496,7 +686,13 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
     p.scale_log2 = scale * kLog2e; p.keep = keep;
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
-    if (g_vcr_flash_warps.load(std::memory_order_relaxed) == 4) {
+    const int org = g_vcr_flash_warps.load(std::memory_order_relaxed);
+    if (org == 1) {
+        if (mode == 0) return launch_attn<3, 0, 2, true>(tq, tk, tv, p, stream);
+        if (mode == 1) return launch_attn<1, 0, 2, true>(tq, tk, tv, p, stream);
+        return launch_attn<1, 1, 2, true>(tq, tk, tv, p, stream);
+    }
+    if (org == 4) {
         if (mode == 0) return launch_attn<3, 0, 4>(tq, tk, tv, p, stream);
         if (mode == 1) return launch_attn<1, 0, 4>(tq, tk, tv, p, stream);
         return launch_attn<1, 1, 4>(tq, tk, tv, p, stream);
