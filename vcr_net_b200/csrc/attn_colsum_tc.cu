@@ -118,7 +118,10 @@ attn_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     tc::mbar_wait(&s_empty[s], ph ^ 1);
                     tc::tc_fence_after();
                     const uint32_t k_addr = tc::smem_u32(smem + OFF_K + s * K_STAGE);
-                    const uint32_t d0 = tmem_base + s * S_COLS, d1 = d0 + BKV;
+                    // one accumulator: every correction product (hi*lo' + lo*hi', carrying 2^11) first, then the main products,
+                    // the first of them with tcgen05.mma's scale-input-d = 11 (Q and the key tile are resident for the whole
+                    // d_k = 128 product) -- half the TMEM read per tile in both sweeps
+                    const uint32_t d0 = tmem_base + s * S_COLS;
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
                         const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * 2) * TILE);
@@ -127,11 +130,20 @@ attn_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         const uint64_t k_lo = tc::umma_desc_k_sw128(k_addr + (kb * 2 + 1) * TILE);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t acc = (kb | kk) != 0;
                             const uint64_t adv = (uint64_t)(kk * 2);
-                            tc::umma_f16(d0, q_hi + adv, k_hi + adv, idesc, acc);
-                            tc::umma_f16(d1, q_hi + adv, k_lo + adv, idesc, acc);
-                            tc::umma_f16(d1, q_lo + adv, k_hi + adv, idesc, 1);
+                            tc::umma_f16(d0, q_hi + adv, k_lo + adv, idesc, (kb | kk) != 0);
+                            tc::umma_f16(d0, q_lo + adv, k_hi + adv, idesc, 1);
+                        }
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * 2) * TILE);
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * 2) * TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            if ((kb | kk) == 0) tc::umma_f16_scale_d11(d0, q_hi + adv, k_hi + adv, idesc);
+                            else tc::umma_f16(d0, q_hi + adv, k_hi + adv, idesc, 1);
                         }
                     }
                     tc::umma_commit(&s_full[s]);
@@ -167,13 +179,11 @@ attn_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         float x[32];
                         {
                             const uint32_t sa = tmem_base + sb * S_COLS + lane_adr + hf * 64 + cc * 32;
-                            uint32_t r0[32], r1[32];
+                            uint32_t r0[32];
                             tc::tmem_ld_32x32(sa, r0);
-                            tc::tmem_ld_32x32(sa + BKV, r1);
                             tc::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                x[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * sc;
+                            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r0[i]) * sc;
                         }
                         if (key0 + 32 > p.Nk) {
 #pragma unroll

@@ -13,8 +13,10 @@
 // TMEM read-modify-write of O is rare.
 //
 // Precision: NTERMS = 3 is the fp32-parity mode -- Q, K, V and P are carried as fp16 (hi, lo*2^11) pairs,
-// each product is hi*hi + 2^-11 (hi*lo + lo*hi) with main and correction terms in separate TMEM
-// accumulators (see gemm_tc.cu).  NTERMS = 1: single fp16 / bf16 pass.
+// each product is hi*hi + 2^-11 (hi*lo + lo*hi).  O keeps main and correction terms in separate TMEM
+// accumulators (see gemm_tc.cu) because it accumulates across key tiles; S = Q K_j^T is complete within one
+// tile, so its correction products are issued first and the first main product rescales the accumulator with
+// tcgen05.mma's scale-input-d = 11: one accumulator, half the per-tile TMEM read.  NTERMS = 1: single fp16 / bf16 pass.
 // Optional key mask keep[B,Nk] (partial overlap, model/transformer.py:48-52): masked keys get -1e9.
 #include <atomic>
 #include "tc_common.cuh"
@@ -183,22 +185,43 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tc::mbar_wait(&s_empty[s], ph ^ 1);
                 tc::tc_fence_after();
                 const uint32_t k_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE);
-                const uint32_t d0 = tmem_base + s * C_::S_COLS, d1 = d0 + BKV;
+                const uint32_t d0 = tmem_base + s * C_::S_COLS;
+                if (NTERMS == 3) {
+                    // Q and K_j are both resident for the whole product (d_k = 128 = two k-blocks), so every correction term
+                    // (hi*lo' + lo*hi', carrying 2^11) goes first and the main terms follow into the SAME accumulator, the
+                    // first of them with scale-input-d = 11: S = sum hi*hi' + 2^-11 sum corr, one 64-column tile to read.
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * PL) * C_::Q_TILE);
-                    const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * PL) * C_::Q_TILE);
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+                        const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * PL + 1) * C_::Q_TILE);
+                        const uint64_t k_lo = tc::umma_desc_k_sw128(k_addr + (kb * PL + 1) * C_::K_TILE);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t acc = (kb | kk) != 0;
-                        const uint64_t adv = (uint64_t)(kk * 2);
-                        tc::umma_f16(d0, q_hi + adv, k_hi + adv, idesc_qk, acc);
-                        if (NTERMS == 3) {
-                            const uint64_t q_lo = tc::umma_desc_k_sw128(q_addr + (kb * PL + 1) * C_::Q_TILE);
-                            const uint64_t k_lo = tc::umma_desc_k_sw128(k_addr + (kb * PL + 1) * C_::K_TILE);
-                            tc::umma_f16(d1, q_hi + adv, k_lo + adv, idesc_qk, acc);
-                            tc::umma_f16(d1, q_lo + adv, k_hi + adv, idesc_qk, 1);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            tc::umma_f16(d0, q_hi + adv, k_lo + adv, idesc_qk, (kb | kk) != 0);
+                            tc::umma_f16(d0, q_lo + adv, k_hi + adv, idesc_qk, 1);
                         }
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * PL) * C_::Q_TILE);
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            if ((kb | kk) == 0) tc::umma_f16_scale_d11(d0, q_hi + adv, k_hi + adv, idesc_qk);
+                            else tc::umma_f16(d0, q_hi + adv, k_hi + adv, idesc_qk, 1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t q_hi = tc::umma_desc_k_sw128(q_addr + (kb * PL) * C_::Q_TILE);
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc::umma_f16(d0, q_hi + (uint64_t)(kk * 2), k_hi + (uint64_t)(kk * 2), idesc_qk, (kb | kk) != 0);
                     }
                 }
                 tc::umma_commit(&s_full[s]);
@@ -287,18 +310,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t sa = tmem_base + sb * C_::S_COLS + lane_adr + h * 32;
                     uint32_t r0[32];
-                    tc::tmem_ld_32x32(sa, r0);
-                    if (NTERMS == 3) {
-                        uint32_t r1[32];
-                        tc::tmem_ld_32x32(sa + BKV, r1);
-                        tc::tmem_ld_wait();
+                    tc::tmem_ld_32x32(sa, r0);                   // one accumulator in every mode (scale-input-d, see issue_qk)
+                    tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) s[h * 32 + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
-                    } else {
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(r0[i]);
-                    }
+                    for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(r0[i]);
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2
@@ -470,18 +485,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     uint32_t r0[CW];
                     if (CW == 32) tc::tmem_ld_32x32(sa, reinterpret_cast<uint32_t(&)[32]>(r0));
                     else tc::tmem_ld_32x16(sa, reinterpret_cast<uint32_t(&)[16]>(r0));
-                    if (NTERMS == 3) {
-                        uint32_t r1[CW];
-                        if (CW == 32) tc::tmem_ld_32x32(sa + BKV, reinterpret_cast<uint32_t(&)[32]>(r1));
-                        else tc::tmem_ld_32x16(sa + BKV, reinterpret_cast<uint32_t(&)[16]>(r1));
-                        tc::tmem_ld_wait();
+                    tc::tmem_ld_wait();                          // one accumulator in every mode (scale-input-d, see issue_qk)
 #pragma unroll
-                        for (int i = 0; i < CW; ++i) s[i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i]));
-                    } else {
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < CW; ++i) s[i] = __uint_as_float(r0[i]);
-                    }
+                    for (int i = 0; i < CW; ++i) s[i] = __uint_as_float(r0[i]);
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&s_empty[sb]);                   // S buffer may be overwritten by QK^T of tile j+2

@@ -135,6 +135,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D = A*B + D * 2^-11 (tcgen05.mma's optional scale-input-d immediate): folds the 2^-11 of the 3-term split's correction
+// accumulator into the tensor core when ALL correction products of a tile are issued before its main products, so main
+// and correction terms share ONE TMEM accumulator (half the tcgen05.ld traffic and TMEM columns of a D0 | D1 pair).
+__device__ __forceinline__ void umma_f16_scale_d11(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
