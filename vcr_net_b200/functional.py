@@ -546,12 +546,10 @@ def mha_project_kv(m, xkv_op, B, Nk, mode, dev, k_out=None, vt_out=None):
     return k_v, vt
 
 
-def mha_attend(m, q_v, k_v, vt, B, Nq, Nk, residual, mode, out=None, max_ws_bytes=3 << 30):
-    """softmax(QK^T/sqrt(d_k)) V (+ the partial-overlap key selection, model/transformer.py:29-55), merge heads,
-    linears[3] + residual (:220-224).  q_v / k_v / vt: operand-format projections of B batch items."""
-    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+def mha_attention(m, q_v, k_v, vt, B, Nq, Nk, mode, dev, max_ws_bytes=3 << 30):
+    """softmax(QK^T/sqrt(d_k)) V (+ the partial-overlap key selection, model/transformer.py:29-55) with the heads merged:
+    -> operand-format [B*Nq, D].  q_v / k_v / vt: operand-format projections of B batch items."""
     D, h, dk = m.h * m.d_k, m.h, m.d_k
-    dev = residual.device
     scale = 1.0 / math.sqrt(dk)
     att = ops.Operand.empty(B * Nq, D, mode, dev)
     keep = None
@@ -587,12 +585,49 @@ def mha_attend(m, q_v, k_v, vt, B, Nq, Nk, residual, mode, out=None, max_ws_byte
                                     keep=keep[b0:b0 + nb] if keep is not None else None, rows_per_batch=h * Nq)
             ops.gemm_tc(P, vt.rows_view(b0 * D, nb * D), Nq, dk, Nk, nbo=nb, nbi=h, a_off=(h * Nq, Nq, 0, 0),
                         b_off=(D, dk, 0, 0), h=att.rows_view(b0 * Nq, nb * Nq), h_strides=(Nq * att.ld, dk), h_split=dk)
-    if out is None:
-        out = torch.empty((B, Nq, D), dtype=_F32, device=dev)
-    ops.gemm_tc(att, Wt["wo"], B * Nq, D, D, bias=W["bo"], c=out, residual=residual)
     if m.__dict__.get("record_attn", False):
         m.attn = attn_probs_head_sum(q_v, k_v, B, h, Nq, Nk, dk, scale, keep)
+    return att
+
+
+def mha_output(m, att, B, Nq, residual, mode, out=None):
+    """linears[3] of the merged heads + the sublayer's residual (model/transformer.py:220-224, :147-153)."""
+    W, Wt = mha_weights(m), mha_weights_tc(m, mode)
+    D = m.h * m.d_k
+    if out is None:
+        out = torch.empty((B, Nq, D), dtype=_F32, device=residual.device)
+    ops.gemm_tc(att, Wt["wo"], B * Nq, D, D, bias=W["bo"], c=out, residual=residual)
     return out
+
+
+def mha_attend(m, q_v, k_v, vt, B, Nq, Nk, residual, mode, out=None, max_ws_bytes=3 << 30):
+    att = mha_attention(m, q_v, k_v, vt, B, Nq, Nk, mode, residual.device, max_ws_bytes=max_ws_bytes)
+    return mha_output(m, att, B, Nq, residual, mode, out=out)
+
+
+def first_self_attention_pair(enc_layer, dec_layer, tok, B, N, mode, dec_out):
+    """Encoder layer 0's and decoder layer 0's self-attention sublayers of the hoisted loop read the SAME tokens (the cloud's
+    embedding): their QKV projections write the halves of one [2B]-item Q|K / V^T buffer and the attention itself runs as ONE
+    flash launch over 2B items instead of two over B (each (batch, head) item is independent, so the bits do not change).
+    Returns the encoder's sublayer output; the decoder's goes to ``dec_out``."""
+    ea, da = enc_layer.self_attn, dec_layer.self_attn
+    D = ea.h * ea.d_k
+    dev = tok.device
+    if (ea.h, ea.d_k, ea.is_src, da.is_src) != (da.h, da.d_k, False, False) or ea.__dict__.get("record_attn") or \
+            da.__dict__.get("record_attn"):
+        x = mha_tc(ea, _ln_op(enc_layer.sublayer[0].norm, tok, mode), None, B, N, N, tok, mode)
+        mha_tc(da, _ln_op(dec_layer.sublayer[0].norm, tok, mode), None, B, N, N, tok, mode, out=dec_out)
+        return x
+    qk2 = ops.Operand.empty(2 * B * N, 2 * D, mode, dev)
+    vt2 = ops.Operand.empty(2 * B * D, N, mode, dev)
+    mha_project_self(ea, _ln_op(enc_layer.sublayer[0].norm, tok, mode), B, N, mode, dev, qk=qk2.rows_view(0, B * N),
+                     vt=vt2.rows_view(0, B * D))
+    mha_project_self(da, _ln_op(dec_layer.sublayer[0].norm, tok, mode), B, N, mode, dev, qk=qk2.rows_view(B * N, B * N),
+                     vt=vt2.rows_view(B * D, B * D))
+    att = mha_attention(ea, qk2.cols_view(0, D), qk2.cols_view(D, D), vt2, 2 * B, N, N, mode, dev)
+    x = mha_output(ea, att.rows_view(0, B * N), B, N, tok, mode)
+    mha_output(da, att.rows_view(B * N, B * N), B, N, tok, mode, out=dec_out)
+    return x
 
 
 def attn_probs_head_sum(q_v, k_v, B, h, Nq, Nk, dk, scale, keep):
@@ -703,9 +738,14 @@ class TargetInvariants:
         emb_tokens(net.emb_nn, tgt, out=self.emb2[B:])
         tgt_tok = self.emb2[B:]
         # encoder(tgt): memory of the decoder items that hold src
+        l0 = model.decoder.layers[0]
+        self.y1 = torch.empty((2 * B, N, D), dtype=_F32, device=dev)           # [y1(src) | y1(tgt)]
         x = tgt_tok
-        for layer in model.encoder.layers:
-            x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
+        for li, layer in enumerate(model.encoder.layers):
+            if li == 0:      # + decoder layer 0's self-attention sublayer on tgt (same input), one flash launch for both
+                x = first_self_attention_pair(layer, l0, tgt_tok, B, N, mode, self.y1[B:])
+            else:
+                x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
             x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * N, x, mode)
         mem_t = _ln_op(model.encoder.norm, x, mode)
         self.k2, self.vt2 = [], []                                             # per decoder layer: [from enc(tgt) | from enc(src)]
@@ -714,10 +754,7 @@ class TargetInvariants:
             vt2 = ops.Operand.empty(2 * B * D, N, mode, dev)
             mha_project_kv(layer.src_attn, mem_t, B, N, mode, dev, k_out=k2.rows_view(0, B * N), vt_out=vt2.rows_view(0, B * D))
             self.k2.append(k2); self.vt2.append(vt2)
-        # decoder layer 0, sublayer 0 on tgt, and the query projection of sublayer 1
-        l0 = model.decoder.layers[0]
-        self.y1 = torch.empty((2 * B, N, D), dtype=_F32, device=dev)           # [y1(src) | y1(tgt)]
-        mha_tc(l0.self_attn, _ln_op(l0.sublayer[0].norm, tgt_tok, mode), None, B, N, N, tgt_tok, mode, out=self.y1[B:])
+        # decoder layer 0: the query projection of sublayer 1 on tgt (sublayer 0 ran with the encoder's above)
         self.q2 = ops.Operand.empty(2 * B * N, D, mode, dev)                   # [Q(src) | Q(tgt)]
         mha_project_q(l0.src_attn, _ln_op(l0.sublayer[1].norm, self.y1[B:], mode), B * N, mode, dev,
                       out=self.q2.rows_view(B * N, B * N))
@@ -726,7 +763,7 @@ class TargetInvariants:
     def supported(net, src, tgt) -> bool:
         from .model.transformer import Transformer
         return (config.precision != "fp32" and isinstance(net.pointer, Transformer) and src.shape == tgt.shape
-                and len(net.pointer.model.decoder.layers) >= 1)
+                and len(net.pointer.model.decoder.layers) >= 1 and len(net.pointer.model.encoder.layers) >= 1)
 
 
 def emb_tokens(emb_nn, xyz, out=None):
@@ -750,8 +787,11 @@ def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False, want_
     src_tok = inv.emb2[:B]
     # encoder(src): memory of the decoder items that hold tgt
     x = src_tok
-    for layer in model.encoder.layers:
-        x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
+    for li, layer in enumerate(model.encoder.layers):
+        if li == 0:          # + decoder layer 0's self-attention sublayer on src (same input), one flash launch for both
+            x = first_self_attention_pair(layer, model.decoder.layers[0], src_tok, B, N, mode, inv.y1[:B])
+        else:
+            x = mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, x, mode), None, B, N, N, x, mode)
         x = ffn_tc(layer.feed_forward, _ln_op(layer.sublayer[1].norm, x, mode), B * N, x, mode)
     mem_s = _ln_op(model.encoder.norm, x, mode)
     y = None
@@ -759,8 +799,7 @@ def transformer_tokens_hoisted(tr, inv: TargetInvariants, want_head=False, want_
         k2, vt2 = inv.k2[li], inv.vt2[li]
         mha_project_kv(layer.src_attn, mem_s, B, N, mode, dev, k_out=k2.rows_view(B * N, B * N), vt_out=vt2.rows_view(B * D, B * D))
         if li == 0:
-            mha_tc(layer.self_attn, _ln_op(layer.sublayer[0].norm, src_tok, mode), None, B, N, N, src_tok, mode, out=inv.y1[:B])
-            y = inv.y1
+            y = inv.y1                           # sublayer 0 on src ran with the encoder's first layer above
             mha_project_q(layer.src_attn, _ln_op(layer.sublayer[1].norm, y[:B], mode), B * N, mode, dev,
                           out=inv.q2.rows_view(0, B * N))
             q2 = inv.q2
