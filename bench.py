@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the cpu_baseline sample (default: one batch)")
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: where the reference's own code runs (cpu = the contract's reference arm; cuda = the "
+                         "stock PyTorch path of the unmodified reference on this GPU, context only)")
     return ap.parse_args()
 
 
@@ -109,11 +112,11 @@ class CpuArm:
     """Runs in a process where CUDA is hidden (the reference picks 'cuda' whenever torch.cuda.is_available(),
     model/vcrnet_model.py:216)."""
 
-    def __init__(self, cfg, kind):
+    def __init__(self, cfg, kind, device="cpu"):
         import torch
         from oracle import synth
         torch.set_num_threads(os.cpu_count())
-        self.cfg, self.kind, self.torch = cfg, kind, torch
+        self.cfg, self.kind, self.torch, self.device = cfg, kind, torch, device
         lpd = dict(np.load(LPD_WEIGHTS))
         self.ckpt = synth.make_checkpoint(1234, emb_weights=lpd)
         if kind == "reference":
@@ -124,6 +127,7 @@ class CpuArm:
                                             num_points=cfg["num_points"])
             self.net = self.VM.VCRNet(args).eval()
             self.net.load_state_dict(synth.checkpoint_to_torch(self.ckpt), strict=True)
+            self.net = self.net.to(device)
 
     def pairs(self, n, first=0):
         from oracle import synth
@@ -137,7 +141,10 @@ class CpuArm:
         t0 = time.perf_counter()
         if self.kind == "reference":
             with torch.no_grad():
-                self.VM.vcrnetIter(self.net, torch.from_numpy(p["src"]), torch.from_numpy(p["tgt"]), iter=c["iters"])
+                out = self.VM.vcrnetIter(self.net, torch.from_numpy(p["src"]).to(self.device),
+                                         torch.from_numpy(p["tgt"]).to(self.device), iter=c["iters"])
+                if self.device != "cpu":
+                    out[2].cpu()                                    # the loop pulls the poses back (:570-580): includes the sync
         else:
             from oracle import vcr_oracle_torch as OT
             OT.vcrnet_iter(self.ckpt, p["src"], p["tgt"], c["iters"], partial=c["partial"], overlap2=c["overlap2"])
@@ -151,7 +158,10 @@ def run_reference_arm(a, cfg, rank, world):
     if rank != 0:
         return
     kind = cpu_kind(a)
-    arm = CpuArm(cfg, kind)
+    on_gpu = a.ref_device == "cuda"
+    if on_gpu and kind != "reference":
+        raise SystemExit("bench.py: --ref-device cuda needs the staged reference (python -m oracle.build_ref)")
+    arm = CpuArm(cfg, kind, device="cuda" if on_gpu else "cpu")
     n = a.cpu_sample_pairs or cfg["batch"]
     budget_s = 240.0
     times = []
@@ -171,11 +181,13 @@ def run_reference_arm(a, cfg, rank, world):
     cores = os.cpu_count()
     M = int(p["src"].shape[2])
     line = {
-        "impl": "reference", "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": a.gpus,
+        "impl": "reference" if not on_gpu else "reference-on-gpu (stock PyTorch, context only)",
+        "metric": "pairs/sec @1024 pts", "value": value, "unit": "pairs/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "batch_per_gpu": n, "num_points": cfg["num_points"], "points_in_net": M,
-                   "iter": cfg["iters"], "precision": "fp32 (torch CPU)", "parallelism": "host cores of rank 0 only",
+                   "iter": cfg["iters"], "precision": "fp32 (torch CPU)" if not on_gpu else "fp32 (stock torch CUDA kernels, TF32 off for matmul)",
+                   "parallelism": "host cores of rank 0 only" if not on_gpu else "one GPU, the reference's own nn.Module path",
                    "weights": "synthetic 59-key checkpoint"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
                          "sample": f"{n} pairs per step ({'the GPU arm batch' if n == cfg['batch'] else 'a bounded sample'}) "
@@ -186,19 +198,27 @@ def run_reference_arm(a, cfg, rank, world):
     emit(line)
 
 
-def cpu_baseline_subprocess(a, cfg, pairs):
-    """cpu_baseline leg of the GPU arm: one pass in a child process with CUDA hidden; returns the child's cpu_baseline dict."""
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+def cpu_baseline_subprocess(a, cfg, pairs, device="cpu", steps=1, warmup=0):
+    """cpu_baseline leg of the GPU arm: one pass in a child process with CUDA hidden; returns the child's cpu_baseline dict.
+    device="cuda": the same child runs the reference's stock PyTorch path on this GPU instead (context only)."""
+    env = dict(os.environ)
+    if device == "cpu":
+        env["CUDA_VISIBLE_DEVICES"] = ""
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
               "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", cfg["key"], "--steps", "1",
-           "--warmup", "0", "--cpu-sample-pairs", str(pairs), "--cpu-kind", a.cpu_kind,
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", cfg["key"], "--steps", str(steps),
+           "--warmup", str(warmup), "--cpu-sample-pairs", str(pairs), "--cpu-kind", a.cpu_kind, "--ref-device", device,
            "--num-points", str(cfg["num_points"]), "--batch", str(cfg["batch"])]
     try:
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         line = json.loads(r.stdout.strip().splitlines()[-1])
         cb = line["cpu_baseline"]
+        if device != "cpu":
+            return {"value": line["value"], "unit": "pairs/s", "ms_per_step": line["ms_per_step"], "batch": pairs,
+                    "what": "the unmodified reference's own vcrnetIter on THIS GPU through stock PyTorch CUDA kernels "
+                            "(oracle/_ref; fp32, cuDNN/cuBLAS defaults), device-resident inputs, poses pulled back per step; "
+                            "context only -- the contract's reference arm is the CPU path"}
         cb["sample"] = (f"{pairs} pairs of the same workload, one pass ({line['ms_per_step'] / 1e3:.1f} s) through "
                         + cb["sample"].split("through ", 1)[1])
         return cb
@@ -635,6 +655,8 @@ def run_gpu_arm(a, cfg, rank, world, local_rank):
         if "whole" in other:
             a1 = argparse.Namespace(**vars(a)); a1.batch = 0; a1.num_points = 0
             other["whole"]["cpu_baseline"] = cpu_baseline_subprocess(a, workload_cfg(a1, "whole", world), 16)
+        if cpu_kind(a) == "reference" and not a.no_other_workloads:
+            line["reference_on_this_gpu"] = cpu_baseline_subprocess(a, cfg, cfg["batch"], device="cuda", steps=5, warmup=2)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -658,7 +680,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.impl == "reference":
+    if a.impl == "reference" and a.ref_device == "cpu":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""        # before torch is imported: the reference must stay on the host cores
     if a.gpus > 1 and "WORLD_SIZE" not in os.environ and a.impl != "reference":
         # launched as plain `python bench.py --gpus N`: re-exec one rank per GPU

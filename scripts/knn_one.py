@@ -8,6 +8,6 @@ x3 = torch.rand(24, 3, 768, device="cuda") - 0.5
 xf = torch.randn(24, 768, 64, device="cuda")
 xop = ops.to_operand(xf.view(-1, 64), "h3")
 for _ in range(2):
-    ops.knn_topk(x3, 20, token_major=False)
+    ops.knn_topk(xf, 20, token_major=True)
     ops.knn_topk_tc(xf, xop, 20)
 torch.cuda.synchronize()
