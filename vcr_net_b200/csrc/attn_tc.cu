@@ -279,7 +279,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int qq = warp & 3, grp = (warp - 4) >> 2;
         const int rloc = qq * 32 + lane;
         const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
-        const int obf = p.out_bf16;
+        constexpr int obf = FMT;              // output / P format is the operand format: compile-time, no per-element branches
         uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
         float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // [0,128): reference maximum, [128,384): l exchange
         auto quarter_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory"); };
@@ -456,7 +456,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int qq = warp & 3, hf = (warp - 4) >> 2;
         const int rloc = qq * 32 + lane;
         const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
-        const int obf = p.out_bf16;
+        constexpr int obf = FMT;              // output / P format is the operand format: compile-time, no per-element branches
         uint8_t* p_smem = smem + C_::OFF_P + rloc * 128;
         float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // NWQ = 2: [2 slots][2][128]; l exchange: [NWQ][128]
         int* mxk = reinterpret_cast<int*>(smem + C_::OFF_XCH);          // NWQ = 4: [3 slots][128] ordered keys

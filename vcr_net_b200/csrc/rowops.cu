@@ -115,6 +115,13 @@ lpd_point_mlp_kernel(const float* __restrict__ xyz, const float* __restrict__ w1
 // ---------------------------------------------------------------------------------------------
 // EXTRA: also write the row in operand format (fp16 hi / lo * 2^11 planes) and its squared norm -- the two things the
 // VCP head derives from the Transformer output (to_operand + sqnorm_rows), with the summation order of sqnorm_rows_kernel.
+// n / den with the reciprocal taken once per row: q = n * r, one Newton step on the residual (the sequence the IEEE division
+// routine runs after its range checks): correctly rounded for normal-range operands, 3 instructions instead of ~10 per element
+__device__ __forceinline__ float div_by(float n, float den, float rcp) {
+    const float q = n * rcp;
+    return fmaf(fmaf(-q, den, n), rcp, q);
+}
+
 template <int VPL, bool EXTRA>  // float4 per lane
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
                                  const float* __restrict__ b, float eps, int M, int D,
@@ -140,6 +147,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
     }
     const float stdv = sqrtf(warp_sum(q) / (float)(D - 1));
     const float den = stdv + eps;
+    const float rcp = 1.f / den;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
     float4* o = reinterpret_cast<float4*>(out + (size_t)row * ldo);
@@ -148,10 +156,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
     for (int i = 0; i < VPL; ++i) {
         const float4 aa = a4[lane + i * 32], bb = b4[lane + i * 32];
         float4 r;
-        r.x = aa.x * v[i].x / den + bb.x;
-        r.y = aa.y * v[i].y / den + bb.y;
-        r.z = aa.z * v[i].z / den + bb.z;
-        r.w = aa.w * v[i].w / den + bb.w;
+        r.x = div_by(aa.x * v[i].x, den, rcp) + bb.x;
+        r.y = div_by(aa.y * v[i].y, den, rcp) + bb.y;
+        r.z = div_by(aa.z * v[i].z, den, rcp) + bb.z;
+        r.w = div_by(aa.w * v[i].w, den, rcp) + bb.w;
         if (rr) {
             const float4 e = rr[lane + i * 32];
             r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
@@ -241,10 +249,11 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int slabs, i
 // Operand-format producers for the tensor-core GEMMs (gemm_tc.cu): LayerNorm and softmax write the
 // 16-bit hi/lo planes directly, so no separate conversion pass sits between them and the next GEMM.
 // ---------------------------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, int PLANES, int BF16>
 __global__ void layernorm_operand_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
                                          const float* __restrict__ b, float eps, int M, int D,
-                                         __half* __restrict__ out, int ldo, long long plane, int planes, int bf16) {
+                                         __half* __restrict__ out, int ldo, long long plane) {
+    constexpr int planes = PLANES, bf16 = BF16;        // compile-time: no per-element format branches
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -264,6 +273,7 @@ __global__ void layernorm_operand_kernel(const float* __restrict__ x, int ldx, c
         q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
     const float den = sqrtf(warp_sum(q) / (float)(D - 1)) + eps;
+    const float rcp = 1.f / den;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
     __half* o = out + (size_t)row * ldo;
@@ -271,8 +281,8 @@ __global__ void layernorm_operand_kernel(const float* __restrict__ x, int ldx, c
     for (int i = 0; i < VPL; ++i) {
         const float4 aa = a4[lane + i * 32], bb = b4[lane + i * 32];
         float4 r;
-        r.x = aa.x * v[i].x / den + bb.x; r.y = aa.y * v[i].y / den + bb.y;
-        r.z = aa.z * v[i].z / den + bb.z; r.w = aa.w * v[i].w / den + bb.w;
+        r.x = div_by(aa.x * v[i].x, den, rcp) + bb.x; r.y = div_by(aa.y * v[i].y, den, rcp) + bb.y;
+        r.z = div_by(aa.z * v[i].z, den, rcp) + bb.z; r.w = div_by(aa.w * v[i].w, den, rcp) + bb.w;
         const int c = (lane + i * 32) * 4;
         *reinterpret_cast<uint2*>(o + c) = make_uint2(tc::pack_h2(r.x, r.y, bf16), tc::pack_h2(r.z, r.w, bf16));
         if (planes == 2)
@@ -851,7 +861,11 @@ VCR_API int vcr_layernorm_operand(const float* x, int ldx, const float* a, const
     dim3 g(vcr_cdiv(M, wpb));
     __half* o = reinterpret_cast<__half*>(out);
     switch (D / 128) {
-#define LN_CASE(V) case V: layernorm_operand_kernel<V><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, o, ldo, plane_stride, planes, bf16); break;
+#define LN_CASE(V) case V: \
+        if (planes == 2) layernorm_operand_kernel<V, 2, 0><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, o, ldo, plane_stride); \
+        else if (bf16) layernorm_operand_kernel<V, 1, 1><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, o, ldo, plane_stride); \
+        else layernorm_operand_kernel<V, 1, 0><<<g, wpb * 32, 0, stream>>>(x, ldx, a, b, eps, (int)M, D, o, ldo, plane_stride); \
+        break;
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
     }
