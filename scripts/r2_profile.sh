@@ -8,7 +8,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 python scripts/summarize_launches.py gpurun_out/launches_partial_h3.csv > gpurun_out/launches_partial_h3_summary.txt
 head -40 gpurun_out/launches_partial_h3_summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:gemm_tc|flash_attn|knn_select|knn3_kernel|edgeconv_dg_tc|attn_colsum|softcorr_tc|layernorm_operand' -s 200 -c 40 \
+    -k 'regex:gemm_tc|flash_attn|knn_select|knn3_kernel|edgeconv_dg_tc|attn_colsum|softcorr_tc|layernorm_operand|select_stats|layernorm_kernel' -s 160 -c 44 \
     -f -o /tmp/prof_h3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-workloads > gpurun_out/ncu_full.log 2>&1
 ncu -i /tmp/prof_h3.ncu-rep --page raw --csv > gpurun_out/prof_h3_raw.csv 2>> gpurun_out/ncu_full.log
 python scripts/summarize_ncu_full.py gpurun_out/prof_h3_raw.csv > gpurun_out/ncu_full_summary.txt
