@@ -116,8 +116,10 @@ int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const void* K, 
                       const void* VT, int ldv, long long v_plane, int B, int H, int Nq, int Nk, int dk,
                       int mode, float scale, const uint8_t* keep, void* O, int ldo, long long o_plane,
                       float* lse, cudaStream_t stream);
-/* Softmax organisation of vcr_flash_attn_tc: 2 (default) = 8 warps on every key tile, 4 = 16 warps, 1 = two groups of 4
- * warps alternating key tiles (a thread owns a whole 64-key row of its tile).  Process-wide; returns the previous setting. */
+/* Organisation of vcr_flash_attn_tc: 3 (default) = Q and P in tensor memory (tcgen05.mma with the A operand in TMEM; P is
+ * written over the S tile it came from), 8 softmax warps; 2 = every operand in shared memory, 8 warps on every key tile
+ * (same bits as 3); 4 = 16 warps; 1 = two groups of 4 warps alternating key tiles.  Process-wide tuning knob; returns the
+ * previous setting. */
 int vcr_set_flash_warps(int nwq);
 /* Process-wide policy for the mode-0 GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 128 tile per pair of SMs, each
  * CTA staging half of the B tile): 0 never, 1 always, 2 auto (default: pairs except for the residual epilogue at

@@ -739,10 +739,10 @@ def _attn_operands(q, k, v, mode):
     return ops.to_operand(tok(q), mode), ops.to_operand(tok(k), mode), ops.to_operand(vt, mode)
 
 
-@pytest.fixture(params=[1, 2, 4], ids=["tile-ping-pong", "8-warps-per-tile", "16-warps-per-tile"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["tile-ping-pong", "8-warps-per-tile", "operands-in-tmem", "16-warps-per-tile"])
 def flash_warps(request):
-    """The softmax organisations of the flash attention kernel: two groups of 4 warps alternating key tiles (default), 8 or
-    16 warps on every tile."""
+    """The organisations of the flash attention kernel: two groups of 4 warps alternating key tiles, 8 warps on every tile with
+    every operand in shared memory, 8 warps with Q and P in tensor memory, 16 warps on every tile."""
     old = ops.set_flash_warps(request.param)
     yield request.param
     ops.set_flash_warps(old)

@@ -68,10 +68,11 @@ gemm_pair = os.environ.get("VCR_GEMM_PAIR", "auto")
 GEMM_PAIR_CODES = {"0": 0, "1": 1, "auto": 2}
 
 
-# flash attention softmax organisation: 2 (default) = 8 softmax warps on every key tile (384 threads per CTA), 4 = 16 (640),
-# 1 = two groups of 4 warps alternating key tiles (measured slower in the parity mode); applied to the library when it is
-# loaded, switchable with ops.set_flash_warps()
-flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "2"))
+# flash attention organisation: 3 (default) = Q and P held in tensor memory (only K and V tiles are read from shared memory
+# by the tensor core), 8 softmax warps; 2 = every operand in shared memory, 8 warps; 4 = 16 warps; 1 = two groups of 4 warps
+# alternating key tiles.  2 and 3 give the same bits.  Applied to the library when it is loaded, switchable with
+# ops.set_flash_warps()
+flash_warps = int(os.environ.get("VCR_FLASH_WARPS", "3"))
 
 
 # vcrnetIter: serve repeated calls of one (network, shapes, iter) from a captured CUDA graph (vcr_net_b200/graph.py;

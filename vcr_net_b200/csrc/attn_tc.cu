@@ -47,7 +47,7 @@ struct ACfg {
     static constexpr int P_TILE = BQ * 128;                     // [128 rows][64 keys]  16 KB
     static constexpr int Q_BYTES = 2 * PL * Q_TILE;             // 2 k-blocks of d_k
     static constexpr int KV_STAGE = 2 * PL * K_TILE + PL * V_TILE;
-    static constexpr int P_BYTES = PL * P_TILE;
+    static constexpr int P_BYTES = 2 * P_TILE;                  // P (hi | lo); also the write-out staging area of the 8 softmax warps (8 x 4 KB)
     static constexpr int NSTAGE = 2;
     static constexpr int OFF_KV = Q_BYTES;
     static constexpr int OFF_P = OFF_KV + NSTAGE * KV_STAGE;
@@ -60,23 +60,11 @@ struct ACfg {
     static constexpr int TMEM_COLS = NTERMS == 3 ? 512 : 256;
 };
 
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // NWQ = softmax warps per TMEM lane quarter (2: a warp owns 32 key columns of its 32 rows, 384 threads; 4: 16 columns,
 // 640 threads).  The softmax is a chain of dependent phases (TMEM load, max, exchange, exp2, split, store) per tile, and
@@ -367,9 +355,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * o_factor);
-                        tmem_st_32x32(oa, r);
+                        tc::tmem_st_32x32(oa, r);
                     }
-                    tmem_st_wait();
+                    tc::tmem_st_wait();
                     tc::tc_fence_before();
                 }
                 // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: 8 16-byte chunks per plane ----
@@ -551,9 +539,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
-                        tmem_st_32x32(oa, r);
+                        tc::tmem_st_32x32(oa, r);
                     }
-                    tmem_st_wait();
+                    tc::tmem_st_wait();
                     tc::tc_fence_before();
                 }
                 // ---- P (fp16 hi / lo*2^11) into the swizzled K-major A-operand tile: CW / 8 16-byte chunks per plane ----
@@ -595,6 +583,58 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const bool q_ok = q < p.Nq;
             const float inv_l = 1.f / l;
             const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + hf * OW;
+            if constexpr (NWQ == 2) {
+                // A thread owns 64 columns of one query row: written straight from registers, every 16-byte store of a warp
+                // lands in a different 128-byte line (32 L1 wavefronts per instruction, ~6 us per item: the whole per-item
+                // bubble of the kernel).  Staged through this warp's 4 KB of the (idle) P buffer instead, swizzled like the P
+                // tile, and read back so that a store instruction covers 4 complete rows of 128 bytes.
+                float v[OW];
+#pragma unroll
+                for (int c = 0; c < OW; c += 32) {
+                    uint32_t r0[32];
+                    tc::tmem_ld_32x32(oa + c, r0);
+                    if (NTERMS == 3) {
+                        uint32_t r1[32];
+                        tc::tmem_ld_32x32(oa + DK + c, r1);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            v[c + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
+                    } else {
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[c + i] = __uint_as_float(r0[i]) * inv_l;
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(o_empty);                         // O is in registers: P V_0 of the next item may overwrite it
+                uint8_t* stg = smem + C_::OFF_P + (hf * 4 + qq) * 4096;          // [32 rows][128 B]
+                const int q0 = qt * BQ + qq * 32;
+                __half* obase = p.O + ((size_t)b * p.Nq + q0) * p.ldo + hh * DK + hf * OW + (lane & 7) * 8;
+#pragma unroll
+                for (int pl = 0; pl < PL; ++pl) {
+#pragma unroll
+                    for (int c = 0; c < OW / 8; ++c) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float a0 = v[c * 8 + 2 * t], a1 = v[c * 8 + 2 * t + 1];
+                            wv[t] = pl == 0 ? tc::pack_h2(a0, a1, obf) : tc::pack_h2(tc::lo_part(a0, obf), tc::lo_part(a1, obf), obf);
+                        }
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3);
+                        const uint4 x = *reinterpret_cast<const uint4*>(stg + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+                        if (q0 + row < p.Nq) *reinterpret_cast<uint4*>(obase + (size_t)row * p.ldo + pl * p.o_plane) = x;
+                    }
+                    __syncwarp();
+                }
+                if (p.lse && q_ok && hf == 0) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
+                continue;                                         // (the next P store of this row quarter follows a pair barrier)
+            }
             __half* orow = p.O + ((size_t)b * p.Nq + q) * p.ldo + hh * DK + hf * OW;
 #pragma unroll 1
             for (int c = 0; c < OW; c += OC) {
@@ -640,6 +680,406 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 2) tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Organisation 3 ("operands in TMEM"): the A side of BOTH products lives in tensor memory.
+// tcgen05.mma reads a shared-memory A operand once per instruction, and the 3-term split issues 24 QK^T instructions of
+// 128x64x16 per key tile: 6 KB of operand reads per 32-cycle instruction against a ~128 B/cycle shared-memory port, so the
+// all-smem tile costs 2054 cycles of tensor issue against a 1536-cycle floor (scripts/mma_rate.cu, profiles/r02_mma_rate.txt:
+// QK 128x64x16 from smem 1.76x its floor, P V 1.12x; with A in TMEM both run at 1.00x).  Here
+//   Q (hi | lo, 128 TMEM columns) is copied smem -> TMEM once per item by the softmax warps (tcgen05.st), and
+//   P is written by tcgen05.st straight over the S tile it was computed from (fp16 pairs: hi 32 | lo 32 columns),
+// so only K_j and V_j are read from shared memory by the tensor core, the P tile no longer crosses shared memory at all, and
+// the Q staging buffer is free for the NEXT item's Q as soon as the copy is done.  TMEM: S/P 2 x 64 | O 2 x 128 | Q 128 = 512.
+// An S buffer is reused by Q K_{j+2}^T, which is issued after P V_j (same thread, the tensor pipe runs in issue order), so no
+// "S empty" barrier is needed; P V_j completion is only waited for in the rare O rescale.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NTERMS>
+struct TCfg {
+    static constexpr int PL = NTERMS == 3 ? 2 : 1;
+    static constexpr int Q_TILE = BQ * 128, K_TILE = BKV * 128, V_TILE = DK * 128;
+    static constexpr int Q_BYTES = 2 * PL * Q_TILE;
+    static constexpr int KV_STAGE = 2 * PL * K_TILE + PL * V_TILE;
+    static constexpr int OFF_KV = Q_BYTES;
+    static constexpr int OFF_STG = OFF_KV + 2 * KV_STAGE;       // write-out staging: 8 warps x 4 KB
+    static constexpr int OFF_BAR = OFF_STG + 8 * 4096;
+    static constexpr int OFF_XCH = OFF_BAR + 256;
+    static constexpr int SLACK = 768;
+    static constexpr int SMEM = OFF_XCH + 2048 + SLACK;
+    static constexpr int O_COL0 = 128;
+    static constexpr int Q_COL0 = O_COL0 + PL * DK;             // plane pl, k-block kb at Q_COL0 + pl * 64 + kb * 32
+};
+
+template <int NTERMS, int FMT, int POLY>
+__global__ void __launch_bounds__(384, 1)
+flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using C_ = TCfg<NTERMS>;
+    constexpr int PL = C_::PL;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    if ((int)(smem - smem_raw) > C_::SLACK) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
+    uint64_t* q_full = bars + 0;  uint64_t* q_empty = bars + 1;  uint64_t* qt_full = bars + 2;
+    uint64_t* k_full = bars + 4;  uint64_t* k_empty = bars + 6;
+    uint64_t* v_full = bars + 8;  uint64_t* v_empty = bars + 10;
+    uint64_t* s_full = bars + 12;
+    uint64_t* p_full = bars + 14; uint64_t* pv_done = bars + 15;
+    uint64_t* o_full = bars + 16; uint64_t* o_empty = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqt = (p.Nq + BQ - 1) / BQ;
+    const int nkv = (p.Nk + BKV - 1) / BKV;
+    const long long items = (long long)p.B * p.H * nqt;
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV); }
+    if (warp == 1 && lane == 0) {
+        tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 256); tc::mbar_init(qt_full, 256);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
+            tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1);
+        }
+        tc::mbar_init(p_full, 256); tc::mbar_init(pv_done, 1);
+        tc::mbar_init(o_full, 1);   tc::mbar_init(o_empty, 256);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (tc::elect_one()) {
+            uint32_t g = 0, w = 0;
+            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+                const int qt = (int)(it % nqt);
+                const int bh = (int)(it / nqt);
+                const int hh = bh % p.H, b = bh / p.H;
+                tc::mbar_wait(q_empty, (w & 1) ^ 1);
+                tc::mbar_expect_tx(q_full, C_::Q_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int pl = 0; pl < PL; ++pl)
+                        tc::tma_load_3d(smem + (kb * PL + pl) * C_::Q_TILE, &tmQ, q_full, hh * DK + kb * 64,
+                                        b * p.Nq + qt * BQ, pl);
+                for (int j = 0; j < nkv; ++j, ++g) {
+                    const int s = g & 1;
+                    uint8_t* st = smem + C_::OFF_KV + s * C_::KV_STAGE;
+                    tc::mbar_wait(&k_empty[s], ((g >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(&k_full[s], 2 * PL * C_::K_TILE);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int pl = 0; pl < PL; ++pl)
+                            tc::tma_load_3d(st + (kb * PL + pl) * C_::K_TILE, &tmK, &k_full[s], hh * DK + kb * 64,
+                                            b * p.Nk + j * BKV, pl);
+                    tc::mbar_wait(&v_empty[s], ((g >> 1) & 1) ^ 1);
+                    tc::mbar_expect_tx(&v_full[s], PL * C_::V_TILE);
+#pragma unroll
+                    for (int pl = 0; pl < PL; ++pl)
+                        tc::tma_load_3d(st + 2 * PL * C_::K_TILE + pl * C_::V_TILE, &tmV, &v_full[s], j * BKV,
+                                        (b * p.H + hh) * DK, pl);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc_qk = tc::umma_idesc(BQ, BKV, FMT);
+            constexpr uint32_t idesc_pv = tc::umma_idesc(BQ, DK, FMT);
+            const uint32_t q_tm = tmem_base + C_::Q_COL0;
+            uint32_t g_qk = 0, g_pv = 0, w = 0;
+            auto issue_qk = [&]() {
+                const int s = g_qk & 1;
+                tc::mbar_wait(&k_full[s], (g_qk >> 1) & 1);
+                tc::tc_fence_after();
+                const uint32_t k_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE);
+                const uint32_t d0 = tmem_base + s * BKV;
+                if (NTERMS == 3) {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+                        const uint64_t k_lo = tc::umma_desc_k_sw128(k_addr + (kb * PL + 1) * C_::K_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            tc::umma_f16_ts(d0, q_tm + kb * 32 + kk * 8, k_lo + adv, idesc_qk, (kb | kk) != 0);
+                            tc::umma_f16_ts(d0, q_tm + 64 + kb * 32 + kk * 8, k_hi + adv, idesc_qk, 1);
+                        }
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            if ((kb | kk) == 0) tc::umma_f16_ts_scale_d11(d0, q_tm, k_hi + adv, idesc_qk);
+                            else tc::umma_f16_ts(d0, q_tm + kb * 32 + kk * 8, k_hi + adv, idesc_qk, 1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t k_hi = tc::umma_desc_k_sw128(k_addr + (kb * PL) * C_::K_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc::umma_f16_ts(d0, q_tm + kb * 32 + kk * 8, k_hi + (uint64_t)(kk * 2), idesc_qk, (kb | kk) != 0);
+                    }
+                }
+                tc::umma_commit(&s_full[s]);
+                tc::umma_commit(&k_empty[s]);
+                ++g_qk;
+            };
+            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+                tc::mbar_wait(qt_full, w & 1);
+                tc::tc_fence_after();
+                issue_qk();
+                for (int j = 0; j < nkv; ++j) {
+                    if (j + 1 < nkv) issue_qk();
+                    const int s = g_pv & 1;
+                    tc::mbar_wait(p_full, g_pv & 1);
+                    tc::mbar_wait(&v_full[s], (g_pv >> 1) & 1);
+                    if (j == 0) tc::mbar_wait(o_empty, (w & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t v_addr = tc::smem_u32(smem + C_::OFF_KV + s * C_::KV_STAGE + 2 * PL * C_::K_TILE);
+                    const uint32_t o0 = tmem_base + C_::O_COL0, o1 = o0 + DK;
+                    const uint32_t p_tm = tmem_base + s * BKV;                    // P over S: hi 32 columns | lo 32 columns
+                    const uint64_t v_hi = tc::umma_desc_k_sw128(v_addr);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (j | kk) != 0;
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        tc::umma_f16_ts(o0, p_tm + kk * 8, v_hi + adv, idesc_pv, acc);
+                        if (NTERMS == 3) {
+                            const uint64_t v_lo = tc::umma_desc_k_sw128(v_addr + C_::V_TILE);
+                            tc::umma_f16_ts(o1, p_tm + kk * 8, v_lo + adv, idesc_pv, acc);
+                            tc::umma_f16_ts(o1, p_tm + 32 + kk * 8, v_hi + adv, idesc_pv, 1);
+                        }
+                    }
+                    tc::umma_commit(&v_empty[s]);
+                    tc::umma_commit(pv_done);
+                    ++g_pv;
+                }
+                tc::umma_commit(o_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================== softmax + output (8 warps, two per TMEM lane quarter) ==============================
+        // warp w owns query rows (TMEM lanes) 32*(w%4)..+32 and key columns 32*hf..+32 of the tile, hf = (w-4)/4.  (Four warps
+        // per quarter with 16 columns each measured 0.95x: the tile is not paced by the length of a warp's chain.)
+        constexpr int CW = BKV / 2, OW = DK / 2;
+        const int qq = warp & 3, hf = (warp - 4) >> 2;
+        const int rloc = qq * 32 + lane;
+        const uint32_t lane_adr = (uint32_t)(qq * 32) << 16;
+        constexpr int obf = FMT;
+        float* xch = reinterpret_cast<float*>(smem + C_::OFF_XCH);      // [2 slots][2][128] maxima; l exchange [2][128]
+        auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory"); };
+        // Q of item number w: smem staging (row rloc, k-block hf, every plane) -> TMEM
+        auto copy_q = [&](uint32_t w) {
+            tc::mbar_wait(q_full, w & 1);
+#pragma unroll
+            for (int pl = 0; pl < PL; ++pl) {
+                const int kb = hf;
+                const uint8_t* row = smem + (kb * PL + pl) * C_::Q_TILE + rloc * 128;
+                uint32_t r[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 x = *reinterpret_cast<const uint4*>(row + ((c ^ (rloc & 7)) * 16));
+                    r[4 * c] = x.x; r[4 * c + 1] = x.y; r[4 * c + 2] = x.z; r[4 * c + 3] = x.w;
+                }
+                tc::tmem_st_32x32(tmem_base + C_::Q_COL0 + lane_adr + pl * 64 + kb * 32, r);
+            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(qt_full);
+            tc::mbar_arrive(q_empty);
+        };
+        uint32_t g = 0, w = 0;
+        if ((long long)blockIdx.x < items) copy_q(0);
+        for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
+            const int qt = (int)(it % nqt);
+            const int bh = (int)(it / nqt);
+            const int hh = bh % p.H, b = bh / p.H;
+            const uint8_t* keep = p.keep ? p.keep + (size_t)b * p.Nk : nullptr;
+            float m_used = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int sb = g & 1;
+                uint32_t km = 0xffffffffu;
+                if (keep != nullptr) {
+                    const int key = j * BKV + hf * CW + lane;
+                    km = __ballot_sync(0xffffffffu, key < p.Nk && __ldg(keep + key) != 0);
+                }
+                tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
+                tc::tc_fence_after();
+                const uint32_t s_tm = tmem_base + sb * BKV + lane_adr;
+                float s[CW];
+                {
+                    uint32_t r0[CW];
+                    tc::tmem_ld_32x32(s_tm + hf * CW, r0);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) s[i] = __uint_as_float(r0[i]);
+                }
+                const int key0 = j * BKV + hf * CW;
+                float sc = p.scale_log2;
+                if (keep != nullptr || j * BKV + BKV > p.Nk) {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        float x = s[i] * sc;
+                        const int key = key0 + i;
+                        if (key >= p.Nk) x = -INFINITY;
+                        else if (!((km >> i) & 1u)) x = -1e9f * kLog2e;
+                        s[i] = x;
+                    }
+                    sc = 1.f;
+                }
+                float mt;
+                {
+                    float m4[4] = {s[0], s[1], s[2], s[3]};       // four independent chains
+#pragma unroll
+                    for (int i = 4; i < CW; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+                    mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+                }
+                {
+                    float* slot = xch + (g & 1) * 256;
+                    slot[hf * 128 + rloc] = mt;
+                    pair_bar();                                   // also: both warps of the quarter have read their S columns
+                    mt = fmaxf(mt, slot[(hf ^ 1) * 128 + rloc]);
+                }
+                float factor = 1.f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mt;
+                } else if (mt > m_used + kRescaleThreshold) {
+                    factor = ex2_approx(m_used - mt);
+                    m_used = mt;
+                    need = true;
+                }
+                const float neg_m = -m_used;
+                float rs0 = 0.f, rs1 = 0.f;
+                // MUFU.EX2 runs at 8 lanes / clock / SM: the 64 exponentials of a row would hold the XU pipe for half the tile's
+                // tensor time, in the middle of the dependent chain that paces the tile; every POLY-th one goes to the FMA pipe
+#pragma unroll
+                for (int i = 0; i < CW; i += 2) {
+                    s[i] = tc::ex2_mix<POLY>(fmaf(s[i], sc, neg_m), i);         rs0 += s[i];
+                    s[i + 1] = tc::ex2_mix<POLY>(fmaf(s[i + 1], sc, neg_m), i + 1); rs1 += s[i + 1];
+                }
+                l = l * factor + (rs0 + rs1);
+                if (__any_sync(0xffffffffu, need)) {              // rare: O may only be touched once P V of the previous tile retired
+                    tc::mbar_wait(pv_done, (g & 1) ^ 1);
+                    tc::tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < PL * OW; c += 32) {
+                        const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + (c >= OW ? DK - OW : 0) + hf * OW + c;
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32(oa, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+                        tc::tmem_st_32x32(oa, r);
+                    }
+                }
+                // ---- P (fp16 hi / lo * 2^11 pairs) over this warp's share of the S tile ----
+                {
+                    uint32_t ph[CW / 2];
+#pragma unroll
+                    for (int i = 0; i < CW / 2; ++i) ph[i] = tc::pack_h2(s[2 * i], s[2 * i + 1], obf);
+                    tc::tmem_st_32x16(s_tm + hf * (CW / 2), ph);
+                    if (NTERMS == 3) {
+#pragma unroll
+                        for (int i = 0; i < CW / 2; ++i) ph[i] = tc::pack_h2(tc::lo_part(s[2 * i], obf), tc::lo_part(s[2 * i + 1], obf), obf);
+                        tc::tmem_st_32x16(s_tm + 32 + hf * (CW / 2), ph);
+                    }
+                }
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                tc::mbar_arrive(p_full);
+            }
+            // ---- item done: combine the partial sums, prefetch-copy the next Q, O / l -> operand-format output ----
+            pair_bar();
+            xch[hf * 128 + rloc] = l;
+            pair_bar();
+            l += xch[(hf ^ 1) * 128 + rloc];
+            pair_bar();
+            if (it + gridDim.x < items) copy_q(w + 1);            // every Q K^T of this item has retired (s_full of its last tile)
+            tc::mbar_wait(o_full, w & 1);
+            tc::tc_fence_after();
+            const int q = qt * BQ + rloc;
+            const bool q_ok = q < p.Nq;
+            const float inv_l = 1.f / l;
+            const uint32_t oa = tmem_base + C_::O_COL0 + lane_adr + hf * OW;
+            float v[OW];
+#pragma unroll
+            for (int c = 0; c < OW; c += 32) {
+                uint32_t r0[32];
+                tc::tmem_ld_32x32(oa + c, r0);
+                if (NTERMS == 3) {
+                    uint32_t r1[32];
+                    tc::tmem_ld_32x32(oa + DK + c, r1);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        v[c + i] = fmaf(__uint_as_float(r1[i]), 1.f / 2048.f, __uint_as_float(r0[i])) * inv_l;
+                } else {
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[c + i] = __uint_as_float(r0[i]) * inv_l;
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(o_empty);
+            uint8_t* stg = smem + C_::OFF_STG + (hf * 4 + qq) * 4096;            // [32 rows][128 B], this warp's
+            const int q0 = qt * BQ + qq * 32;
+            __half* obase = p.O + ((size_t)b * p.Nq + q0) * p.ldo + hh * DK + hf * OW + (lane & 7) * 8;
+#pragma unroll
+            for (int pl = 0; pl < PL; ++pl) {
+#pragma unroll
+                for (int c = 0; c < OW / 8; ++c) {
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a0 = v[c * 8 + 2 * t], a1 = v[c * 8 + 2 * t + 1];
+                        wv[t] = pl == 0 ? tc::pack_h2(a0, a1, obf) : tc::pack_h2(tc::lo_part(a0, obf), tc::lo_part(a1, obf), obf);
+                    }
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + (lane >> 3);
+                    const uint4 x = *reinterpret_cast<const uint4*>(stg + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+                    if (q0 + row < p.Nq) *reinterpret_cast<uint4*>(obase + (size_t)row * p.ldo + pl * p.o_plane) = x;
+                }
+                __syncwarp();
+            }
+            if (p.lse && q_ok && hf == 0) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+template <int NTERMS, int FMT, int POLY>
+int launch_attn_ts(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
+    using C_ = TCfg<NTERMS>;
+    auto kern = flash_attn_ts_kernel<NTERMS, FMT, POLY>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long items = (long long)p.B * p.H * ((p.Nq + BQ - 1) / BQ);
+    const int grid = (int)(items < sms ? items : sms);
+    kern<<<grid, 384, C_::SMEM, st>>>(tq, tk, tv, p);
+    VCR_CHECK_LAUNCH();
+    return VCR_OK;
+}
+
 template <int NTERMS, int FMT, int NWQ, bool PING = false>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
     using C_ = ACfg<NTERMS>;
@@ -657,15 +1097,18 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 }  // namespace
 
-static std::atomic<int> g_vcr_flash_warps{2};      // tuning knob (see vcr_set_flash_warps)
+static std::atomic<int> g_vcr_flash_warps{3};      // tuning knob (see vcr_set_flash_warps)
+static std::atomic<int> g_vcr_flash_poly{0};
+// tuning knob (diagnostic, not part of the header): every n-th exponential of organisation 3 on the FMA pipe (0 = none; 2, 3, 4)
+VCR_API int vcr_debug_set_flash_poly(int n) { return g_vcr_flash_poly.exchange(n == 2 || n == 3 || n == 4 ? n : 0); }
 
-// Softmax organisation of the flash attention kernel: 2 (default) = 8 warps on every tile, two per TMEM lane quarter
-// splitting the key columns (384 threads); 4 = 16 warps, four per quarter (640 threads); 1 = two groups of 4 warps
-// alternating key tiles, a thread owning a whole 64-key row of its tile (built in round 2 to overlap consecutive tiles'
-// softmax chains; measured 0.90-0.95x in the parity mode, 1.04x in single-pass fp16 -- profiles/r02_flash_organisations.txt
-// -- so it is not the default).  Process-wide; returns the previous setting.  Results agree to fp32 rounding of the row sums.
+// Organisation of the flash attention kernel: 3 (default) = Q and P in tensor memory, 8 softmax warps (flash_attn_ts_kernel);
+// 2 = every operand in shared memory, 8 warps on every tile, two per TMEM lane quarter splitting the key columns; 4 = 16
+// warps, four per quarter; 1 = two groups of 4 warps alternating key tiles.  Measured at 48 x 4 x 768 x 768 in the parity
+// mode (profiles/r02_flash_organisations.txt): 139.5 / 155.1 / 176.3 / 176.0 us.  Process-wide; returns the previous setting.
+// 2 and 3 are bit-identical; the others agree to fp32 rounding of the row sums.
 VCR_API int vcr_set_flash_warps(int nwq) {
-    return g_vcr_flash_warps.exchange(nwq == 4 ? 4 : (nwq == 2 ? 2 : 1));
+    return g_vcr_flash_warps.exchange(nwq >= 1 && nwq <= 4 ? nwq : 3);
 }
 
 // Q: operand buffer [planes][B*Nq][ldq], head hh in columns [hh*128, hh*128+128) of the given base;
@@ -693,6 +1136,19 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.scale_log2 = scale * kLog2e; p.keep = keep;
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
     const int org = g_vcr_flash_warps.load(std::memory_order_relaxed);
+    if (org == 3) {
+        const int poly = g_vcr_flash_poly.load(std::memory_order_relaxed);
+#define VCR_TS_CASE(P) \
+    if (poly == P) { \
+        if (mode == 0) return launch_attn_ts<3, 0, P>(tq, tk, tv, p, stream); \
+        if (mode == 1) return launch_attn_ts<1, 0, P>(tq, tk, tv, p, stream); \
+        return launch_attn_ts<1, 1, P>(tq, tk, tv, p, stream); \
+    }
+        VCR_TS_CASE(2) VCR_TS_CASE(3) VCR_TS_CASE(4)
+        VCR_TS_CASE(0)
+#undef VCR_TS_CASE
+        return VCR_ERR_INVALID;
+    }
     if (org == 1) {
         if (mode == 0) return launch_attn<3, 0, 2, true>(tq, tk, tv, p, stream);
         if (mode == 1) return launch_attn<1, 0, 2, true>(tq, tk, tv, p, stream);

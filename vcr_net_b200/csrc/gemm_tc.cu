@@ -329,29 +329,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
                 if (t_fast) {
-                    // lane = output column col0 + lane; it gathers the 32 rows of that column (conflict-free:
-                    // for a fixed row the swizzle maps the 32 columns onto 32 distinct banks)
-                    const float bz = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
-                    float x[32];
+                    // Four lanes per output column, 8 consecutive rows (16 bytes per plane) each: a store instruction covers
+                    // 8 columns x 64 contiguous bytes of V^T (one lane per column, 4 x 16 B each, cost 32 L1 wavefronts per
+                    // instruction and made the epilogue of a V^T tile as long as its K = 512 main loop).  The rows are read
+                    // in an order rotated by 2 * (lane & 3) so that the four lanes of a column, which share the swizzle
+                    // pattern, hit different banks; the packed row pairs are rotated back with selects.
+                    const int q = lane & 3, cs = lane >> 2;
 #pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) {
-                        float y = fmaf(alpha, stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)], bz);
-                        x[rr] = act == 1 ? leaky(y, slope) : y;
-                    }
-                    __half* tt = Tz + (size_t)(col0 + lane - h_split) * p.ldt + row0;
+                    for (int i = 0; i < 4; ++i) {
+                        const int cl = cs + 8 * i;                                    // column of the chunk
+                        const float bz = p.bias ? __ldg(p.bias + col0 + cl) : 0.f;
+                        uint32_t wh[4], wl[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(tt + q * 8) =
-                            make_uint4(pack_h2(x[q * 8 + 0], x[q * 8 + 1], obf), pack_h2(x[q * 8 + 2], x[q * 8 + 3], obf),
-                                       pack_h2(x[q * 8 + 4], x[q * 8 + 5], obf), pack_h2(x[q * 8 + 6], x[q * 8 + 7], obf));
-                    if (nplanes == 2) {
+                        for (int m = 0; m < 4; ++m) {
+                            const int rp = (m + q) & 3;                               // row pair held by word m
+                            const int rr = q * 8 + 2 * rp;
+                            float y0 = fmaf(alpha, stg[rr * 32 + (((cl >> 2) ^ (rr & 7)) << 2) + (cl & 3)], bz);
+                            float y1 = fmaf(alpha, stg[(rr + 1) * 32 + (((cl >> 2) ^ ((rr + 1) & 7)) << 2) + (cl & 3)], bz);
+                            if (act == 1) { y0 = leaky(y0, slope); y1 = leaky(y1, slope); }
+                            wh[m] = pack_h2(y0, y1, obf);
+                            wl[m] = pack_h2(lo_part(y0, obf), lo_part(y1, obf), obf);
+                        }
+                        // word j of the store = row pair j = wh[(j - q) & 3]
+                        uint32_t th[4], tl[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<uint4*>(tt + p.t_plane + q * 8) =
-                                make_uint4(pack_h2(lo_part(x[q * 8 + 0], obf), lo_part(x[q * 8 + 1], obf), obf),
-                                           pack_h2(lo_part(x[q * 8 + 2], obf), lo_part(x[q * 8 + 3], obf), obf),
-                                           pack_h2(lo_part(x[q * 8 + 4], obf), lo_part(x[q * 8 + 5], obf), obf),
-                                           pack_h2(lo_part(x[q * 8 + 6], obf), lo_part(x[q * 8 + 7], obf), obf));
+                        for (int j = 0; j < 4; ++j) {
+                            th[j] = (q & 1) ? wh[(j + 3) & 3] : wh[j];
+                            tl[j] = (q & 1) ? wl[(j + 3) & 3] : wl[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            wh[j] = (q & 2) ? th[(j + 2) & 3] : th[j];
+                            wl[j] = (q & 2) ? tl[(j + 2) & 3] : tl[j];
+                        }
+                        __half* tt = Tz + (size_t)(col0 + cl - h_split) * p.ldt + row0 + q * 8;
+                        *reinterpret_cast<uint4*>(tt) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                        if (nplanes == 2) *reinterpret_cast<uint4*>(tt + p.t_plane) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
                     }
                 }
                 if (rowmajor && fast && row0 + 32 <= M) {

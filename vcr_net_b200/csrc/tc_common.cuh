@@ -27,6 +27,37 @@ __device__ __forceinline__ float lo_part(float x, int bf16) {
     return (x - __half2float(__float2half_rn(x))) * 2048.f;
 }
 
+// ---------------------------------------------------------------- exp2 -------------------------------
+// MUFU.EX2 issues 8 lanes / clock / SM on sm_100a (measured: the key statistic kernel, two exp2 per score, ran at the XU
+// pipe's limit -- profiles/r02_ncu_attn_xu.txt), half the tensor-core time of a 3-term score tile.  The attention kernels
+// therefore evaluate a fixed share of their exponentials on the FMA pipe instead: Cody-Waite split y = n + f, f in
+// [-0.5, 0.5], degree-6 minimax polynomial for 2^f (max relative error 7.9e-8, below ex2.approx's 2^-22), exponent add.
+// y <= 0 expected (scores minus the row maximum); anything below -126 (masked keys, -inf) gives ~2^-126.
+__device__ __forceinline__ float ex2_mufu(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_fma(float y) {
+    y = fmaxf(y, -126.f);
+    const float t = y + 12582912.f;                      // 1.5 * 2^23: round(y) in the low mantissa bits
+    const float f = y - (t - 12582912.f);
+    float p = 0x1.41d32ap-13f;
+    p = fmaf(p, f, 0x1.5f456ap-10f);
+    p = fmaf(p, f, 0x1.3b2dbcp-7f);
+    p = fmaf(p, f, 0x1.c6aed4p-5f);
+    p = fmaf(p, f, 0x1.ebfbdap-3f);
+    p = fmaf(p, f, 0x1.62e430p-1f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// element i of an unrolled loop: every POLY-th exponential (POLY = 0: none) goes to the FMA pipe
+template <int POLY>
+__device__ __forceinline__ float ex2_mix(float y, int i) {
+    if (POLY > 0 && (i % POLY) == POLY - 1) return ex2_fma(y);
+    return ex2_mufu(y);
+}
+
 // ---------------------------------------------------------------- mbarrier --------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -150,6 +181,46 @@ __device__ __forceinline__ void umma_f16_scale_d11(uint32_t tmem_d, uint64_t des
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// A operand in tensor memory (lane = row, 16-bit elements packed two per 32-bit column: k = 2c in the low half), B from a
+// shared-memory descriptor
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_scale_d11(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2) ----------
 // Two CTAs of a cluster (same TPC) execute ONE tcgen05.mma with M = 256: each CTA holds its 128 rows of A and of the
