@@ -17,7 +17,6 @@
 // warp 2 TMEM allocator, warps 4-19 statistics (thread = query row, four warps split the 128 key columns of a tile: the
 // per-tile work of a warp is one dependent chain -- TMEM load, maximum, exp2, sum / transpose-reduce -- and with two warps
 // per scheduler its latency, 2x the tile's tensor time, set the pace; four warps with half the chain each hide it).
-#include <atomic>
 #include "tc_common.cuh"
 
 namespace {
@@ -46,8 +45,6 @@ struct ColsumParams {
 
 __device__ __forceinline__ float ex2_approx(float x) { return tc::ex2_mufu(x); }
 
-// POLY: every POLY-th exponential of a row chunk on the FMA pipe (tc::ex2_mix), 0 = all on MUFU
-template <int POLY>
 __global__ void __launch_bounds__(128 + NSTAT, 1)
 attn_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const ColsumParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -223,12 +220,12 @@ attn_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                             const float nm = -m;
                             float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) a4[i & 3] += tc::ex2_mix<POLY>(fmaf(x[i], sc, nm), i);
+                            for (int i = 0; i < 32; ++i) a4[i & 3] += ex2_approx(fmaf(x[i], sc, nm));
                             l += (a4[0] + a4[1]) + (a4[2] + a4[3]);
                         } else {
                             const float w = row_ok ? l : 0.f;   // rows past Nq (next batch / padding) contribute nothing
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) x[i] = tc::ex2_mix<POLY>(fmaf(x[i], sc, m), i) * w;
+                            for (int i = 0; i < 32; ++i) x[i] = ex2_approx(fmaf(x[i], sc, m)) * w;
                             // transpose-reduce: afterwards x[0] of lane c is the sum over the warp's 32 rows of column c
 #pragma unroll
                             for (int off = 16; off >= 1; off >>= 1) {
@@ -287,10 +284,6 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int slabs, 
 
 }  // namespace
 
-static std::atomic<int> g_vcr_colsum_poly{4};
-// tuning knob (diagnostic, not part of the header): every n-th exponential of the key statistic on the FMA pipe (0 = none)
-VCR_API int vcr_debug_set_colsum_poly(int n) { return g_vcr_colsum_poly.exchange(n); }
-
 VCR_API size_t vcr_attn_colsum_workspace_bytes(int B, int H, int Nq, int Nk) {
     return (size_t)B * H * ((Nq + BQ - 1) / BQ) * 4 * Nk * sizeof(float);
 }
@@ -311,9 +304,7 @@ VCR_API int vcr_attn_colsum_tc(const void* Q, int ldq, long long q_plane, const 
     ColsumParams p;
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.scale_log2 = scale * kLog2e;
     p.part = reinterpret_cast<float*>(workspace);
-    const int poly = g_vcr_colsum_poly.load(std::memory_order_relaxed);
-    auto kern = poly == 2 ? attn_colsum_tc_kernel<2> : poly == 3 ? attn_colsum_tc_kernel<3> : poly == 4 ? attn_colsum_tc_kernel<4>
-              : poly == 8 ? attn_colsum_tc_kernel<8> : attn_colsum_tc_kernel<0>;
+    auto kern = attn_colsum_tc_kernel;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
         return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;

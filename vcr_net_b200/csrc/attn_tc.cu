@@ -710,7 +710,7 @@ struct TCfg {
     static constexpr int Q_COL0 = O_COL0 + PL * DK;             // plane pl, k-block kb at Q_COL0 + pl * 64 + kb * 32
 };
 
-template <int NTERMS, int FMT, int POLY>
+template <int NTERMS, int FMT>
 __global__ void __launch_bounds__(384, 1)
 flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -962,12 +962,10 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 const float neg_m = -m_used;
                 float rs0 = 0.f, rs1 = 0.f;
-                // MUFU.EX2 runs at 8 lanes / clock / SM: the 64 exponentials of a row would hold the XU pipe for half the tile's
-                // tensor time, in the middle of the dependent chain that paces the tile; every POLY-th one goes to the FMA pipe
 #pragma unroll
                 for (int i = 0; i < CW; i += 2) {
-                    s[i] = tc::ex2_mix<POLY>(fmaf(s[i], sc, neg_m), i);         rs0 += s[i];
-                    s[i + 1] = tc::ex2_mix<POLY>(fmaf(s[i + 1], sc, neg_m), i + 1); rs1 += s[i + 1];
+                    s[i] = ex2_approx(fmaf(s[i], sc, neg_m));         rs0 += s[i];
+                    s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m)); rs1 += s[i + 1];
                 }
                 l = l * factor + (rs0 + rs1);
                 if (__any_sync(0xffffffffu, need)) {              // rare: O may only be touched once P V of the previous tile retired
@@ -1065,10 +1063,10 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int NTERMS, int FMT, int POLY>
+template <int NTERMS, int FMT>
 int launch_attn_ts(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
     using C_ = TCfg<NTERMS>;
-    auto kern = flash_attn_ts_kernel<NTERMS, FMT, POLY>;
+    auto kern = flash_attn_ts_kernel<NTERMS, FMT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1098,9 +1096,6 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 }  // namespace
 
 static std::atomic<int> g_vcr_flash_warps{3};      // tuning knob (see vcr_set_flash_warps)
-static std::atomic<int> g_vcr_flash_poly{0};
-// tuning knob (diagnostic, not part of the header): every n-th exponential of organisation 3 on the FMA pipe (0 = none; 2, 3, 4)
-VCR_API int vcr_debug_set_flash_poly(int n) { return g_vcr_flash_poly.exchange(n == 2 || n == 3 || n == 4 ? n : 0); }
 
 // Organisation of the flash attention kernel: 3 (default) = Q and P in tensor memory, 8 softmax warps (flash_attn_ts_kernel);
 // 2 = every operand in shared memory, 8 warps on every tile, two per TMEM lane quarter splitting the key columns; 4 = 16
@@ -1137,17 +1132,9 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
     const int org = g_vcr_flash_warps.load(std::memory_order_relaxed);
     if (org == 3) {
-        const int poly = g_vcr_flash_poly.load(std::memory_order_relaxed);
-#define VCR_TS_CASE(P) \
-    if (poly == P) { \
-        if (mode == 0) return launch_attn_ts<3, 0, P>(tq, tk, tv, p, stream); \
-        if (mode == 1) return launch_attn_ts<1, 0, P>(tq, tk, tv, p, stream); \
-        return launch_attn_ts<1, 1, P>(tq, tk, tv, p, stream); \
-    }
-        VCR_TS_CASE(2) VCR_TS_CASE(3) VCR_TS_CASE(4)
-        VCR_TS_CASE(0)
-#undef VCR_TS_CASE
-        return VCR_ERR_INVALID;
+        if (mode == 0) return launch_attn_ts<3, 0>(tq, tk, tv, p, stream);
+        if (mode == 1) return launch_attn_ts<1, 0>(tq, tk, tv, p, stream);
+        return launch_attn_ts<1, 1>(tq, tk, tv, p, stream);
     }
     if (org == 1) {
         if (mode == 0) return launch_attn<3, 0, 2, true>(tq, tk, tv, p, stream);

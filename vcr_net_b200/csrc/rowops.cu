@@ -569,9 +569,9 @@ __global__ void negdist_kernel(float* __restrict__ dot, int ld, int Ns, int Nt, 
 //   col_stat = sum_i softmax_j(pd)_ij   (row softmax, summed over rows)    -> picks the target points (:222)
 //   row_stat = sum_j softmax_i(pd)_ij   (column softmax, summed over cols) -> picks the source points (:244)
 // A CTA owns a slab of RS rows of one pair, staged as pd in shared memory.  Pass A: exact row (max, sum exp) per row and
-// per-slab column (max, sum exp) partials; a small kernel combines the slabs per column in slab order; pass B recomputes
-// pd and accumulates both weighted sums (rows complete, columns as per-slab partials reduced in slab order by
-// colsum_final_kernel).  Replaces negdist (R+W) + col_max / col_sum partials + rowsum_colsoftmax + softmax_rows (3R+2W) +
+// per-slab column (max, sum exp) partials; a small kernel combines the slabs per column (8 interleaved slab groups, fixed
+// order); pass B recomputes pd and accumulates both weighted sums (rows complete, columns as per-slab partials reduced the
+// same way by select_stats_final_kernel).  Replaces negdist (R+W) + col_max / col_sum partials + rowsum_colsoftmax + softmax_rows (3R+2W) +
 // colsum: ~9 reads and 3 writes of the [Ns, Nt] matrix become 2 reads.  Deterministic (fixed slab order, no atomics).
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_T = 256;
@@ -639,31 +639,75 @@ select_stats_a_kernel(const float* __restrict__ dot, int ld, int Ns, int Nt, int
         psum[((size_t)b * slabs + slab) * Nt + j] = sacc;
     }
 }
-__global__ void select_stats_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int slabs, int Nt,
-                                            float* __restrict__ cmax, float* __restrict__ csum) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (j >= Nt) return;
+// Per column: (max, sum exp) over the slabs' partials and the reciprocal of the sum.  A CTA owns 32 columns; its 8 warps each
+// scan every 8th slab (coalesced 128-byte rows), and the 8 partial results are combined in warp order -- fixed order, no
+// atomics.  (One thread per column walking all ~100 slabs was a 25 us chain of dependent L2 loads.)
+constexpr int SEL_CG = 8;                   // slab groups (warps) per CTA of the combine / final kernels
+__global__ void __launch_bounds__(32 * SEL_CG)
+select_stats_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int slabs, int Nt,
+                            float* __restrict__ cmax, float* __restrict__ csum, float* __restrict__ crcp) {
+    __shared__ float sm_m[SEL_CG][32], sm_s[SEL_CG][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane, b = blockIdx.y;
+    const bool ok = j < Nt;
+    const float* pm = pmax + (size_t)b * slabs * Nt + j;
+    const float* ps = psum + (size_t)b * slabs * Nt + j;
     float m = -INFINITY;
-    for (int t = 0; t < slabs; ++t) m = fmaxf(m, pmax[((size_t)b * slabs + t) * Nt + j]);
+    if (ok)
+        for (int t = grp; t < slabs; t += SEL_CG) m = fmaxf(m, pm[(size_t)t * Nt]);
+    sm_m[grp][lane] = m;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < SEL_CG; ++g) m = fmaxf(m, sm_m[g][lane]);
     float sacc = 0.f;
-    for (int t = 0; t < slabs; ++t) sacc += psum[((size_t)b * slabs + t) * Nt + j] * expf(pmax[((size_t)b * slabs + t) * Nt + j] - m);
-    cmax[(size_t)b * Nt + j] = m;
-    csum[(size_t)b * Nt + j] = sacc;
+    if (ok)
+        for (int t = grp; t < slabs; t += SEL_CG) sacc += ps[(size_t)t * Nt] * expf(pm[(size_t)t * Nt] - m);
+    sm_s[grp][lane] = sacc;
+    __syncthreads();
+    if (grp == 0 && ok) {
+        float tot = 0.f;
+#pragma unroll
+        for (int g = 0; g < SEL_CG; ++g) tot += sm_s[g][lane];
+        cmax[(size_t)b * Nt + j] = m;
+        csum[(size_t)b * Nt + j] = tot;
+        crcp[(size_t)b * Nt + j] = 1.f / tot;
+    }
+}
+// out[b, j] = sum over slabs of part[b, slab, j]: 8 warps take every 8th slab, partials added in warp order
+__global__ void __launch_bounds__(32 * SEL_CG)
+select_stats_final_kernel(const float* __restrict__ part, int slabs, int Nt, float* __restrict__ out) {
+    __shared__ float sm_s[SEL_CG][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane, b = blockIdx.y;
+    const bool ok = j < Nt;
+    const float* pp = part + (size_t)b * slabs * Nt + j;
+    float sacc = 0.f;
+    if (ok)
+        for (int t = grp; t < slabs; t += SEL_CG) sacc += pp[(size_t)t * Nt];
+    sm_s[grp][lane] = sacc;
+    __syncthreads();
+    if (grp == 0 && ok) {
+        float tot = 0.f;
+#pragma unroll
+        for (int g = 0; g < SEL_CG; ++g) tot += sm_s[g][lane];
+        out[(size_t)b * Nt + j] = tot;
+    }
 }
 template <int NV>
 __global__ void __launch_bounds__(SEL_T)
 select_stats_b_kernel(const float* __restrict__ dot, int ld, int Ns, int Nt, int vec, const float* __restrict__ xx,
                       const float* __restrict__ yy, const float* __restrict__ rmax, const float* __restrict__ rsum,
-                      const float* __restrict__ cmax, const float* __restrict__ csum, float* __restrict__ row_stat,
-                      float* __restrict__ cpart) {
+                      const float* __restrict__ cmax, const float* __restrict__ csum, const float* __restrict__ crcp,
+                      float* __restrict__ row_stat, float* __restrict__ cpart) {
     constexpr int LDP = NV * 128;
     __shared__ __align__(16) float sm[SEL_RS * LDP];
-    __shared__ float s_rm[SEL_RS], s_rs[SEL_RS];
+    __shared__ float s_rm[SEL_RS], s_rs[SEL_RS], s_rr[SEL_RS];
     const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
     const int i0 = slab * SEL_RS, nr = min(SEL_RS, Ns - i0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* cm = cmax + (size_t)b * Nt;
     const float* cs = csum + (size_t)b * Nt;
+    const float* cr = crcp + (size_t)b * Nt;      // 1 / csum: the quotients below are div_by's (correctly rounded, 3 instructions)
     if (warp < nr) {                                       // column softmax, summed along the row (:243-244)
         const int i = i0 + warp;
         float4 v[NV];
@@ -676,18 +720,19 @@ select_stats_b_kernel(const float* __restrict__ dot, int ld, int Ns, int Nt, int
             const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (c + u < Nt) sacc += expf(e[u] - cm[c + u]) / cs[c + u];
+                if (c + u < Nt) sacc += div_by(expf(e[u] - cm[c + u]), cs[c + u], cr[c + u]);
         }
         sacc = warp_sum(sacc);
         if (lane == 0) {
             row_stat[(size_t)b * Ns + i] = sacc;
             s_rm[warp] = rmax[(size_t)b * Ns + i]; s_rs[warp] = rsum[(size_t)b * Ns + i];
+            s_rr[warp] = 1.f / s_rs[warp];
         }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < Nt; j += SEL_T) {        // row softmax, summed down the column (:221-222)
         float sacc = 0.f;
-        for (int r = 0; r < nr; ++r) sacc += expf(sm[r * LDP + j] - s_rm[r]) / s_rs[r];
+        for (int r = 0; r < nr; ++r) sacc += div_by(expf(sm[r * LDP + j] - s_rm[r]), s_rs[r], s_rr[r]);
         cpart[((size_t)b * slabs + slab) * Nt + j] = sacc;
     }
 }
@@ -989,7 +1034,8 @@ VCR_API int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt
     if (!workspace || workspace_bytes < vcr_rowsum_colsoftmax_workspace_bytes(B, Nt)) return VCR_ERR_WORKSPACE;
     float* cmax = reinterpret_cast<float*>(workspace);
     float* csum = cmax + (size_t)B * Nt;
-    float* pmax = csum + (size_t)B * Nt;
+    float* crcp = csum + (size_t)B * Nt;
+    float* pmax = crcp + (size_t)B * Nt;
     float* psum = pmax + (size_t)COL_SLABS * B * Nt;
     dim3 g(vcr_cdiv(Nt, 128), COL_SLABS, B);
     col_max_partial_kernel<<<g, 128, 0, stream>>>(pd, ld, Ns, Nt, pmax);
@@ -1007,7 +1053,7 @@ VCR_API int vcr_rowsum_colsoftmax(const float* pd, int ld, int B, int Ns, int Nt
 
 VCR_API size_t vcr_select_stats_workspace_bytes(int B, int Ns, int Nt) {
     const size_t slabs = (size_t)(Ns + SEL_RS - 1) / SEL_RS;
-    return ((size_t)2 * B * Ns + (size_t)2 * B * Nt + (size_t)3 * B * slabs * Nt) * sizeof(float);
+    return ((size_t)2 * B * Ns + (size_t)3 * B * Nt + (size_t)3 * B * slabs * Nt) * sizeof(float);
 }
 // selectCom's two selection statistics from the score products dot[B, Ns, ld] (left untouched), xx [B, Ns], yy [B, Nt]:
 // row_stat [B, Ns] = row sums of the column softmax of pd, col_stat [B, Nt] = column sums of the row softmax of pd.
@@ -1026,25 +1072,26 @@ VCR_API int vcr_select_stats(const float* dot, int ld, int B, int Ns, int Nt, co
     float* rsum = rmax + (size_t)B * Ns;
     float* cmax = rsum + (size_t)B * Ns;
     float* csum = cmax + (size_t)B * Nt;
-    float* pmax = csum + (size_t)B * Nt;
+    float* crcp = csum + (size_t)B * Nt;
+    float* pmax = crcp + (size_t)B * Nt;
     float* psum = pmax + (size_t)B * slabs * Nt;
     float* cpart = psum + (size_t)B * slabs * Nt;
-    dim3 g(slabs, B), gc(vcr_cdiv(Nt, 128), B);
+    dim3 g(slabs, B), gc(vcr_cdiv(Nt, 32), B);
     switch ((Nt + 127) / 128) {
 #define SEL_CASE(V) case V: select_stats_a_kernel<V><<<g, SEL_T, 0, stream>>>(dot, ld, Ns, Nt, vec, xx, yy, rmax, rsum, pmax, psum); break;
         SEL_CASE(1) SEL_CASE(2) SEL_CASE(3) SEL_CASE(4) SEL_CASE(5) SEL_CASE(6) SEL_CASE(7) SEL_CASE(8)
 #undef SEL_CASE
     }
     VCR_CHECK_LAUNCH();
-    select_stats_combine_kernel<<<gc, 128, 0, stream>>>(pmax, psum, slabs, Nt, cmax, csum);
+    select_stats_combine_kernel<<<gc, 32 * SEL_CG, 0, stream>>>(pmax, psum, slabs, Nt, cmax, csum, crcp);
     VCR_CHECK_LAUNCH();
     switch ((Nt + 127) / 128) {
-#define SEL_CASE(V) case V: select_stats_b_kernel<V><<<g, SEL_T, 0, stream>>>(dot, ld, Ns, Nt, vec, xx, yy, rmax, rsum, cmax, csum, row_stat, cpart); break;
+#define SEL_CASE(V) case V: select_stats_b_kernel<V><<<g, SEL_T, 0, stream>>>(dot, ld, Ns, Nt, vec, xx, yy, rmax, rsum, cmax, csum, crcp, row_stat, cpart); break;
         SEL_CASE(1) SEL_CASE(2) SEL_CASE(3) SEL_CASE(4) SEL_CASE(5) SEL_CASE(6) SEL_CASE(7) SEL_CASE(8)
 #undef SEL_CASE
     }
     VCR_CHECK_LAUNCH();
-    colsum_final_kernel<<<gc, 128, 0, stream>>>(cpart, slabs, Nt, col_stat);
+    select_stats_final_kernel<<<gc, 32 * SEL_CG, 0, stream>>>(cpart, slabs, Nt, col_stat);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }

@@ -28,34 +28,13 @@ __device__ __forceinline__ float lo_part(float x, int bf16) {
 }
 
 // ---------------------------------------------------------------- exp2 -------------------------------
-// MUFU.EX2 issues 8 lanes / clock / SM on sm_100a (measured: the key statistic kernel, two exp2 per score, ran at the XU
-// pipe's limit -- profiles/r02_ncu_attn_xu.txt), half the tensor-core time of a 3-term score tile.  The attention kernels
-// therefore evaluate a fixed share of their exponentials on the FMA pipe instead: Cody-Waite split y = n + f, f in
-// [-0.5, 0.5], degree-6 minimax polynomial for 2^f (max relative error 7.9e-8, below ex2.approx's 2^-22), exponent add.
-// y <= 0 expected (scores minus the row maximum); anything below -126 (masked keys, -inf) gives ~2^-126.
+// (Round 2 tried moving a share of the attention kernels' exponentials to the FMA pipe -- Cody-Waite split + degree-6
+// polynomial, 7.9e-8 relative error -- on the theory that MUFU.EX2 paced the softmax: no gain at any share, in either
+// kernel (profiles/r02_colsum_diag.txt, r02_flash_organisations_v2.txt), so every exponential stays on the XU pipe.)
 __device__ __forceinline__ float ex2_mufu(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-__device__ __forceinline__ float ex2_fma(float y) {
-    y = fmaxf(y, -126.f);
-    const float t = y + 12582912.f;                      // 1.5 * 2^23: round(y) in the low mantissa bits
-    const float f = y - (t - 12582912.f);
-    float p = 0x1.41d32ap-13f;
-    p = fmaf(p, f, 0x1.5f456ap-10f);
-    p = fmaf(p, f, 0x1.3b2dbcp-7f);
-    p = fmaf(p, f, 0x1.c6aed4p-5f);
-    p = fmaf(p, f, 0x1.ebfbdap-3f);
-    p = fmaf(p, f, 0x1.62e430p-1f);
-    p = fmaf(p, f, 1.0f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-// element i of an unrolled loop: every POLY-th exponential (POLY = 0: none) goes to the FMA pipe
-template <int POLY>
-__device__ __forceinline__ float ex2_mix(float y, int i) {
-    if (POLY > 0 && (i % POLY) == POLY - 1) return ex2_fma(y);
-    return ex2_mufu(y);
 }
 
 // ---------------------------------------------------------------- mbarrier --------------------------
