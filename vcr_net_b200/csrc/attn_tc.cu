@@ -909,10 +909,14 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float m_used = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int sb = g & 1;
-                uint32_t km = 0xffffffffu;
-                if (keep != nullptr) {
+                // additive score bias of key (this warp's column `lane`): 0 = kept, -1e9 (log2 domain) = masked, -inf = past Nk;
+                // requested before the wait on S, broadcast column by column with shuffles below
+                const bool biased = keep != nullptr || j * BKV + BKV > p.Nk;      // warp-uniform
+                float bias_l = 0.f;
+                if (biased) {
                     const int key = j * BKV + hf * CW + lane;
-                    km = __ballot_sync(0xffffffffu, key < p.Nk && __ldg(keep + key) != 0);
+                    if (key >= p.Nk) bias_l = -INFINITY;
+                    else if (keep != nullptr && __ldg(keep + key) == 0) bias_l = -1e9f * kLog2e;
                 }
                 tc::mbar_wait(&s_full[sb], (g >> 1) & 1);
                 tc::tc_fence_after();
@@ -925,17 +929,10 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                     for (int i = 0; i < CW; ++i) s[i] = __uint_as_float(r0[i]);
                 }
-                const int key0 = j * BKV + hf * CW;
                 float sc = p.scale_log2;
-                if (keep != nullptr || j * BKV + BKV > p.Nk) {
+                if (biased) {                                     // one shuffle + one fma per score (the bias is the same for every row)
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) {
-                        float x = s[i] * sc;
-                        const int key = key0 + i;
-                        if (key >= p.Nk) x = -INFINITY;
-                        else if (!((km >> i) & 1u)) x = -1e9f * kLog2e;
-                        s[i] = x;
-                    }
+                    for (int i = 0; i < CW; ++i) s[i] = fmaf(s[i], sc, __shfl_sync(0xffffffffu, bias_l, i));
                     sc = 1.f;
                 }
                 float mt;
