@@ -94,10 +94,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int reps, long l
             }
         };
         long long t0 = 0;
+        unsigned long long g0 = 0, g1;
         for (int r = -8; r < reps; ++r) {                             // 8 warm-up rounds
             if (r == 0) {
                 tc::umma_commit(&bar); tc::mbar_wait(&bar, 0);
                 t0 = clock64();
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
             }
             switch (mode) {
                 case 0: qk(r & 1, i64, K_TILE); break;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int reps, long l
         }
         tc::umma_commit(&bar); tc::mbar_wait(&bar, 1);
         cycles[blockIdx.x] = clock64() - t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        cycles[148 + blockIdx.x] = (long long)(g1 - g0);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -241,7 +245,7 @@ int main() {
     printf("A operand in TMEM (lane = row, fp16 pair k = 2c, 2c+1 in column c): %s (%d mismatches)\n", bad ? "MISMATCH" : "exact", bad);
     // ---- rates ----
     long long* d_cyc;
-    cudaMalloc(&d_cyc, 148 * 8);
+    cudaMalloc(&d_cyc, 2 * 148 * 8);
     const char* names[] = {"24 x QK 128x64x16 SS", "12 x PV 128x128x16 SS", "12 x 128x256x16 SS", "12 x PV 128x128x16, A in TMEM",
                            "tile: 24 QK(N=64) + 12 PV, all SS", "tile: 24 QK(N=64) SS + 12 PV A-in-TMEM", "24 x QK 128x128x16 SS",
                            "128 keys: 24 QK(N=128) + 24 PV, all SS", "128 keys: 24 QK(N=128) SS + 24 PV A-in-TMEM",
@@ -249,15 +253,15 @@ int main() {
     const int floors[] = {24 * 32, 12 * 64, 12 * 128, 12 * 64, 24 * 32 + 12 * 64, 24 * 32 + 12 * 64, 24 * 64, 24 * 64 + 24 * 64, 24 * 64 + 24 * 64, 24 * 32, 24 * 32 + 12 * 64};
     for (int grid : {1, 148})
         for (int mode = 0; mode < 11; ++mode) {
-            const int reps = 400;
+            const int reps = grid == 1 ? 400 : 40000;                 // the full-chip runs are long enough (tens of ms) for the power cap to act
             rate_kernel<<<grid, 128, SMEM>>>(mode, reps, d_cyc);
-            std::vector<long long> c(grid);
-            e = cudaMemcpy(c.data(), d_cyc, grid * 8, cudaMemcpyDeviceToHost);
+            std::vector<long long> c(296);
+            e = cudaMemcpy(c.data(), d_cyc, 296 * 8, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { printf("rate_kernel mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
-            double s = 0;
-            for (long long x : c) s += (double)x;
-            s /= grid * (double)reps;
-            printf("grid %3d  %-46s %8.1f cycles   floor %5d   x%.2f\n", grid, names[mode], s, floors[mode], s / floors[mode]);
+            double s = 0, ns = 0;
+            for (int b = 0; b < grid; ++b) { s += (double)c[b]; ns += (double)c[148 + b]; }
+            printf("grid %3d  %-46s %8.1f cycles   floor %5d   x%.2f   SM clock %.2f GHz\n", grid, names[mode], s / (grid * (double)reps), floors[mode],
+                   s / (grid * (double)reps) / floors[mode], s / ns);
         }
     cudaFuncSetAttribute(port_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     long long* d_c2;
