@@ -787,6 +787,30 @@ def test_flash_attention_shapes_and_rescale(Nq, Nk, spread, flash_warps):
     assert np.abs(nump(lse) - ref_lse).max() < 1e-3 * max(1.0, np.abs(ref_lse).max())
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_flash_attention_several_items_per_cta_into_a_dirty_buffer(masked, flash_warps):
+    """More work items (10 x 4 x 6 = 240) than SMs, so every persistent CTA walks the item boundary code (next Q, O write-out,
+    barrier phases), and an output buffer pre-filled with NaN, so a row that is not written cannot hide behind stale data."""
+    rs = np.random.RandomState(11)
+    B, h, Nq, Nk, dk = 10, 4, 768, 320, 128
+    q = rs.randn(B, h, Nq, dk).astype(np.float32)
+    k = rs.randn(B, h, Nk, dk).astype(np.float32)
+    v = rs.randn(B, h, Nk, dk).astype(np.float32)
+    kept = (rs.rand(B, Nk) < 0.7).astype(np.uint8) if masked else None
+    sc = (q.astype(np.float64) @ k.astype(np.float64).transpose(0, 1, 3, 2)) / np.sqrt(dk)
+    if masked:
+        sc = np.where(kept[:, None, None, :] != 0, sc, -1e9)
+    p = np.exp(sc - sc.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
+    want = (p @ v.astype(np.float64)).transpose(0, 2, 1, 3).reshape(B * Nq, h * dk)
+    Q, K, VT = _attn_operands(q, k, v, "h3")
+    out = ops.Operand.empty(B * Nq, h * dk, "h3", DEV)
+    out.buf.view(torch.int16).fill_(0x7E00)                       # fp16 NaN in both planes
+    ops.flash_attn_tc(Q, K, VT, out, B, h, Nq, Nk, dk, 1.0 / np.sqrt(dk), keep=cu(kept) if masked else None)
+    got = nump(out.to_float())
+    assert np.isfinite(got).all()
+    assert rel_err(got, want) < 3e-5
+
+
 # ---------------------------------------------------------------- SURVEY 8(f): embeddings / heads variants ----------
 def _load_prefixed(module, g, prefix):
     sd = {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items()

@@ -701,7 +701,8 @@ struct TCfg {
     static constexpr int Q_BYTES = 2 * PL * Q_TILE;
     static constexpr int KV_STAGE = 2 * PL * K_TILE + PL * V_TILE;
     static constexpr int OFF_KV = Q_BYTES;
-    static constexpr int OFF_BAR = OFF_KV + 2 * KV_STAGE;
+    static constexpr int OFF_STG = OFF_KV + 2 * KV_STAGE;       // write-out staging: 8 warps x 4 KB
+    static constexpr int OFF_BAR = OFF_STG + 8 * 4096;
     static constexpr int OFF_XCH = OFF_BAR + 256;
     static constexpr int SLACK = 768;
     static constexpr int SMEM = OFF_XCH + 2048 + SLACK;
@@ -712,7 +713,7 @@ struct TCfg {
 template <int NTERMS, int FMT>
 __global__ void __launch_bounds__(384, 1)
 flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using C_ = TCfg<NTERMS>;
     constexpr int PL = C_::PL;
     extern __shared__ uint8_t smem_raw[];
@@ -732,9 +733,7 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int nkv = (p.Nk + BKV - 1) / BKV;
     const long long items = (long long)p.B * p.H * nqt;
 
-    if (warp == 0 && lane == 0) {
-        tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV); tc::tma_prefetch_desc(&tmO);
-    }
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV); }
     if (warp == 1 && lane == 0) {
         tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 256); tc::mbar_init(qt_full, 256);
         for (int s = 0; s < 2; ++s) {
@@ -756,10 +755,11 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // ============================== TMA producer ==============================
         if (tc::elect_one()) {
             uint32_t g = 0, w = 0;
-            auto load_q = [&](long long it) {                   // Q of an item into the staging tiles
+            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
                 const int qt = (int)(it % nqt);
                 const int bh = (int)(it / nqt);
                 const int hh = bh % p.H, b = bh / p.H;
+                tc::mbar_wait(q_empty, (w & 1) ^ 1);
                 tc::mbar_expect_tx(q_full, C_::Q_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
@@ -767,11 +767,6 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int pl = 0; pl < PL; ++pl)
                         tc::tma_load_3d(smem + (kb * PL + pl) * C_::Q_TILE, &tmQ, q_full, hh * DK + kb * 64,
                                         b * p.Nq + qt * BQ, pl);
-            };
-            if ((long long)blockIdx.x < items) load_q(blockIdx.x);
-            for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
-                const int bh = (int)(it / nqt);
-                const int hh = bh % p.H, b = bh / p.H;
                 for (int j = 0; j < nkv; ++j, ++g) {
                     const int s = g & 1;
                     uint8_t* st = smem + C_::OFF_KV + s * C_::KV_STAGE;
@@ -789,12 +784,6 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int pl = 0; pl < PL; ++pl)
                         tc::tma_load_3d(st + 2 * PL * C_::K_TILE + pl * C_::V_TILE, &tmV, &v_full[s], j * BKV,
                                         (b * p.H + hh) * DK, pl);
-                    // next item's Q, a whole item ahead of its use: the staging tiles are free once this item's Q is in TMEM and
-                    // the previous item's O, staged in the same tiles, has been read by its TMA stores (q_empty, see below)
-                    if (j == (nkv > 3 ? 3 : nkv - 1) && it + gridDim.x < items) {   // (q_empty arrives at this item's tile 1)
-                        tc::mbar_wait(q_empty, w & 1);
-                        load_q(it + gridDim.x);
-                    }
                 }
             }
         }
@@ -908,19 +897,10 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(qt_full);
-        };
-        // The O tile of an item is staged in this warp's OWN blocks of the Q staging tiles (rows 32 qq.. of tiles (hf, pl):
-        // exactly what copy_q reads) and leaves by TMA store; q_empty -- the producer may load the next Q -- is signalled once
-        // those stores have read their source, which is checked a key tile later so that nobody waits for it.
-        bool stores_pending = false;
-        auto release_q_staging = [&]() {
-            if (lane == 0) tc::bulk_wait_read_all();
-            __syncwarp();
             tc::mbar_arrive(q_empty);
-            stores_pending = false;
         };
         uint32_t g = 0, w = 0;
-        if ((long long)blockIdx.x < items) { copy_q(0); tc::mbar_arrive(q_empty); }
+        if ((long long)blockIdx.x < items) copy_q(0);
         for (long long it = blockIdx.x; it < items; it += gridDim.x, ++w) {
             const int qt = (int)(it % nqt);
             const int bh = (int)(it / nqt);
@@ -929,7 +909,6 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float m_used = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int sb = g & 1;
-                if (stores_pending && j == (nkv > 1 ? 1 : 0)) release_q_staging();
                 // additive score bias of key (this warp's column `lane`): 0 = kept, -1e9 (log2 domain) = masked, -inf = past Nk;
                 // requested before the wait on S, broadcast column by column with shuffles below
                 const bool biased = keep != nullptr || j * BKV + BKV > p.Nk;      // warp-uniform
@@ -1049,10 +1028,11 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             tc::tc_fence_before();
             tc::mbar_arrive(o_empty);
-            if (stores_pending) release_q_staging();             // (single-tile items: not yet released in the loop)
+            uint8_t* stg = smem + C_::OFF_STG + (hf * 4 + qq) * 4096;            // [32 rows][128 B], this warp's
+            const int q0 = qt * BQ + qq * 32;
+            __half* obase = p.O + ((size_t)b * p.Nq + q0) * p.ldo + hh * DK + hf * OW + (lane & 7) * 8;
 #pragma unroll
             for (int pl = 0; pl < PL; ++pl) {
-                uint8_t* stg = smem + (hf * PL + pl) * C_::Q_TILE + qq * 4096;   // [32 rows][128 B], 128-byte swizzle
 #pragma unroll
                 for (int c = 0; c < OW / 8; ++c) {
                     uint32_t wv[4];
@@ -1063,19 +1043,17 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                     *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 }
-            }
-            tc::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {                                      // rows past Nq of this batch item are clipped by the 4-d map
+                __syncwarp();
 #pragma unroll
-                for (int pl = 0; pl < PL; ++pl)
-                    tc::tma_store_4d(&tmO, smem + (hf * PL + pl) * C_::Q_TILE + qq * 4096, hh * DK + hf * OW, qt * BQ + qq * 32, b, pl);
-                tc::bulk_commit();
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + (lane >> 3);
+                    const uint4 x = *reinterpret_cast<const uint4*>(stg + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+                    if (q0 + row < p.Nq) *reinterpret_cast<uint4*>(obase + (size_t)row * p.ldo + pl * p.o_plane) = x;
+                }
+                __syncwarp();
             }
-            stores_pending = true;
             if (p.lse && q_ok && hf == 0) p.lse[((size_t)b * p.H + hh) * p.Nq + q] = m_used + log2f(l);
         }
-        if (stores_pending && lane == 0) tc::bulk_wait_read_all();   // the staging tiles outlive their last stores
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1083,8 +1061,7 @@ flash_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 template <int NTERMS, int FMT>
-int launch_attn_ts(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, const AttnParams& p,
-                   cudaStream_t st) {
+int launch_attn_ts(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
     using C_ = TCfg<NTERMS>;
     auto kern = flash_attn_ts_kernel<NTERMS, FMT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM) != cudaSuccess) return VCR_ERR_LAUNCH;
@@ -1093,7 +1070,7 @@ int launch_attn_ts(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long items = (long long)p.B * p.H * ((p.Nq + BQ - 1) / BQ);
     const int grid = (int)(items < sms ? items : sms);
-    kern<<<grid, 384, C_::SMEM, st>>>(tq, tk, tv, to, p);
+    kern<<<grid, 384, C_::SMEM, st>>>(tq, tk, tv, p);
     VCR_CHECK_LAUNCH();
     return VCR_OK;
 }
@@ -1152,12 +1129,9 @@ VCR_API int vcr_flash_attn_tc(const void* Q, int ldq, long long q_plane, const v
     p.O = reinterpret_cast<__half*>(O); p.ldo = ldo; p.o_plane = o_plane; p.lse = lse; p.out_bf16 = mode == 2;
     const int org = g_vcr_flash_warps.load(std::memory_order_relaxed);
     if (org == 3) {
-        CUtensorMap to;
-        rc = vcr_make_operand_tmap_batched(&to, O, H * DK, Nq, B, ldo, o_plane, planes, 32);
-        if (rc != VCR_OK) return rc;
-        if (mode == 0) return launch_attn_ts<3, 0>(tq, tk, tv, to, p, stream);
-        if (mode == 1) return launch_attn_ts<1, 0>(tq, tk, tv, to, p, stream);
-        return launch_attn_ts<1, 1>(tq, tk, tv, to, p, stream);
+        if (mode == 0) return launch_attn_ts<3, 0>(tq, tk, tv, p, stream);
+        if (mode == 1) return launch_attn_ts<1, 0>(tq, tk, tv, p, stream);
+        return launch_attn_ts<1, 1>(tq, tk, tv, p, stream);
     }
     if (org == 1) {
         if (mode == 0) return launch_attn<3, 0, 2, true>(tq, tk, tv, p, stream);

@@ -586,23 +586,6 @@ int vcr_make_operand_tmap(CUtensorMap* out, const void* base, int cols, long lon
     return r == CUDA_SUCCESS ? VCR_OK : VCR_ERR_INVALID;
 }
 
-int vcr_make_operand_tmap_batched(CUtensorMap* out, const void* base, int cols, int rows_per_batch, int batches, int ld_elems,
-                                  long long plane_stride_elems, int planes, int box_rows) {
-    vcr_tmap_encode_fn enc = vcr_get_tmap_encoder();
-    if (!enc) return VCR_ERR_LAUNCH;
-    if ((ld_elems & 7) || (reinterpret_cast<uintptr_t>(base) & 15) || (plane_stride_elems & 7)) return VCR_ERR_INVALID;
-    const long long rows = (long long)rows_per_batch * batches;
-    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows_per_batch, (cuuint64_t)batches, (cuuint64_t)(planes > 0 ? planes : 1)};
-    cuuint64_t strides[3] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)ld_elems * 2 * (cuuint64_t)rows_per_batch,
-                             (cuuint64_t)(planes > 1 ? plane_stride_elems : (long long)ld_elems * rows) * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? VCR_OK : VCR_ERR_INVALID;
-}
-
 // Tensor-core GEMM on operand-format inputs.
 //   A: [a_planes][a_rows_total][lda] 16-bit, B likewise (both K-major).  mode: 0 = fp16 split 3-term ("h3"),
 //   1 = fp16 single, 2 = bf16 single.  Per batch z = (zo, zi): A rows start at zo*a_row_o + zi*a_row_i and its

@@ -84,16 +84,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// TMA store of a smem tile (bulk async group of the issuing thread); the tile must be fenced (fence.proxy.async) first
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// every bulk store this thread committed has finished READING its shared-memory source
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
 // ---------------------------------------------------------------- TMEM ------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
@@ -282,7 +272,3 @@ vcr_tmap_encode_fn vcr_get_tmap_encoder();
 // box = 64 elements (128 B) x box_rows x 1, 128-B swizzle, zero fill out of bounds.
 int vcr_make_operand_tmap(CUtensorMap* out, const void* base, int cols, long long rows, int ld_elems,
                           long long plane_stride_elems, int planes, int box_rows);
-// 4-D map over the same kind of buffer with the rows split as [batches][rows_per_batch] (a TMA store of a row block is then
-// clipped at the end of ITS batch item): dims {cols, rows_per_batch, batches, planes}, box 64 x box_rows x 1 x 1.
-int vcr_make_operand_tmap_batched(CUtensorMap* out, const void* base, int cols, int rows_per_batch, int batches, int ld_elems,
-                                  long long plane_stride_elems, int planes, int box_rows);
