@@ -953,8 +953,13 @@ def vcp_select(src_xyz, src_tok, tgt_xyz, tgt_tok, overlap2, pre=None, want_toke
         pd = ops.negdist_(dot, ld, Ns, Nt, xx, yy)
         row_stat = ops.rowsum_colsoftmax(pd, ld, Ns, Nt)
         col_stat = ops.colsum(ops.softmax_rows_(pd.view(B * Ns, ld)[:, :Nt]), B)
-    idx_t, _ = ops.topk_select(col_stat, tgtK)
-    idx_s, _ = ops.topk_select(row_stat, srcK)
+    both = row_stat._base
+    if srcK == tgtK and both is not None and both is col_stat._base and tuple(both.shape) == (2, B, Ns):
+        idx = ops.topk_select(both.view(2 * B, Ns), srcK)[0]           # both rankings (:222, :244) in one launch
+        idx_s, idx_t = idx[:B], idx[B:]
+    else:
+        idx_t, _ = ops.topk_select(col_stat, tgtK)
+        idx_s, _ = ops.topk_select(row_stat, srcK)
     so, to = ops.gather_cols(src_xyz, idx_s), ops.gather_cols(tgt_xyz, idx_t)
     if pre is not None and not want_tokens:
         s_sel = Selected(*ops.gather_operand_rows(pre[0].op, pre[0].sq, idx_s, B, Ns))

@@ -696,8 +696,12 @@ def select_stats(dot: torch.Tensor, ld: int, Ns: int, Nt: int, xx: torch.Tensor,
     B = dot.shape[0]
     dev = dot.device
     L = lib()
-    row_stat = torch.empty((B, Ns), dtype=_F32, device=dev)
-    col_stat = torch.empty((B, Nt), dtype=_F32, device=dev)
+    if Ns == Nt:                              # one [2, B, N] buffer: the caller can rank both statistics in one launch
+        both = torch.empty((2, B, Ns), dtype=_F32, device=dev)
+        row_stat, col_stat = both[0], both[1]
+    else:
+        row_stat = torch.empty((B, Ns), dtype=_F32, device=dev)
+        col_stat = torch.empty((B, Nt), dtype=_F32, device=dev)
     wsb = L.vcr_select_stats_workspace_bytes(B, Ns, Nt)
     ws = torch.empty(wsb // 4, dtype=_F32, device=dev)
     L.check(L.vcr_select_stats(dot.data_ptr(), ld, B, Ns, Nt, xx.data_ptr(), yy.data_ptr(), row_stat.data_ptr(),
