@@ -4,7 +4,7 @@ usage: python scripts/ncu_traffic.py raw.csv [raw2.csv ...] > profiles/rNN_ncu_t
 import csv, json, re, sys, collections
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
-FAMILY = [("gemm_tc_kernel", "vcr_gemm_tc"), ("flash_attn_tc_kernel", "vcr_flash_attn_tc"), ("knn_select_kernel<16", "vcr_knn_topk[D=64]"),
+FAMILY = [("gemm_tc_kernel", "vcr_gemm_tc"), ("flash_attn_ts_kernel", "vcr_flash_attn_tc"), ("flash_attn_tc_kernel", "vcr_flash_attn_tc"), ("knn_select_kernel<16", "vcr_knn_topk[D=64]"),
           ("knn_select_kernel<(int)16", "vcr_knn_topk[D=64]"), ("knn3_kernel", "vcr_knn_topk[D=3]"),
           ("knn_select_kernel", "vcr_knn_topk[D=3]"), ("layernorm_operand_kernel", "vcr_layernorm_operand"),
           ("knn_tc2_kernel", "vcr_knn_topk_tc"), ("edgeconv_dg_tc_kernel", "vcr_edgeconv_dg_tc"),
