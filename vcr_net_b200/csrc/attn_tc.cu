@@ -2,9 +2,11 @@
 // d_k = 128 without ever writing the [B,h,Nq,Nk] score or probability tensors (reference
 // model/transformer.py:13-55 materialises both in fp32: 2 x 268 MB per call at B=16, N=1024).
 //
+// Two kernels share this file: flash_attn_ts_kernel (the default, further down: Q and P are tcgen05.mma A operands held in
+// TENSOR memory) and flash_attn_tc_kernel (every operand in shared memory, three softmax organisations; kept selectable).
 // Work item = (batch, head, 128-query tile); persistent CTAs walk the items.  Per 64-key tile:
 //   warp 1 (one elected thread)  S = Q K_j^T          tcgen05.mma 128x64x16, S in TMEM (double-buffered)
-//   warps 4-11 (2 threads per query row, 32 keys each) online softmax: tcgen05.ld S -> exp2 -> P (fp16 hi/lo) -> smem
+//   warps 4-11 (2 threads per query row, 32 keys each) online softmax: tcgen05.ld S -> exp2 -> P (fp16 hi/lo) -> smem / TMEM
 //   warp 1                        O += P V_j           tcgen05.mma 128x128x16, O stays in TMEM
 //   warp 0 (one elected thread)  TMA: Q once per item, {K_j, V^T_j} through a 2-stage ring
 // QK^T of tile j+1 is issued before P V of tile j, so the tensor core works while the softmax warps
